@@ -1,0 +1,132 @@
+/*
+ * yololite_b200 -- C ABI of the B200 (sm_100a) engine for YoloLite's detection forward pass + postprocess.
+ *
+ * The reference (Lillthorin/YoloLite-Official-Repo) has no FFI: its boundary is the Python duck type
+ * `model(x) -> list[Tensor]` plus a handful of free functions.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference repo root).  Conventions:
+ *
+ *   - plain pointers and sizes only; every tensor is allocated by the caller (so on the Python side the
+ *     outputs are ordinary torch.Tensors) and passed as a raw DEVICE pointer unless the name says host;
+ *   - the engine owns packed weights and scratch, nothing else;
+ *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*), no host sync inside
+ *     yl_forward / yl_postprocess / yl_preprocess -> graph-capturable;
+ *   - return value 0 = ok, negative = error; the message is in yl_last_error() (thread local);
+ *   - there is NO CPU fallback: every call fails loudly without a CUDA device.
+ */
+#ifndef YOLOLITE_B200_H
+#define YOLOLITE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YL_ABI_VERSION 1
+
+typedef struct yl_engine yl_engine;
+
+/* ---- layer program ------------------------------------------------------------------------------
+ * The host side (Python packer) lowers a reference checkpoint {"state_dict","meta"}
+ * (tools/train.py:62-75, tools/infer.py:80-102) into a flat list of fused ops over numbered NHWC fp32
+ * activation buffers plus one fp32 weight blob with BatchNorm folded into the preceding conv
+ * (scripts/model/model_v2.py:15-53,250-377 and the timm backbone it calls at :266-272).           */
+enum yl_op_kind {
+  YL_OP_STEM = 0,  /* dense 3x3 conv on the NCHW network input (Cin=3) -> NHWC, +bias, act             */
+  YL_OP_CONV = 1,  /* dense KxK conv as implicit GEMM, NHWC -> NHWC; K=1 is the pointwise conv; epilogue:
+                      +bias, +residual buffer, +nearest-upsampled coarser buffer, act, head layout       */
+  YL_OP_DW = 2,    /* depthwise KxK conv (K = 3 or 5), NHWC, +bias, act                                   */
+  YL_OP_DWPW = 3   /* fused DWConvBlock: depthwise 3x3 s1 (no bias) -> pointwise + bias + act
+                      (model_v2.py:23-39); the depthwise result never leaves shared memory               */
+};
+enum yl_act { YL_ACT_NONE = 0, YL_ACT_RELU = 1, YL_ACT_SILU = 2 };
+
+#define YL_SRC_INPUT (-1)          /* op.src: the network input x                                      */
+#define YL_DST_LEVEL(l) (-(1 + (l))) /* op.dst: write output level l ([B,A,S,S,5+C], model_v2.py:340-350) */
+
+typedef struct yl_op {
+  int32_t kind;      /* yl_op_kind */
+  int32_t src;       /* activation buffer id, or YL_SRC_INPUT */
+  int32_t dst;       /* activation buffer id, or YL_DST_LEVEL(l) */
+  int32_t res;       /* buffer id added to the output (same shape) before act, or -1 */
+  int32_t up;        /* buffer id of a coarser map, nearest-resized to the output size and added, or -1 */
+  int32_t cin, cout;
+  int32_t k, stride; /* padding is k/2 */
+  int32_t act;       /* yl_act */
+  int32_t anchors;   /* >0 only for head output convs: cout = anchors*(5+C), stored [B,A,H,W,5+C] */
+  int32_t k2;        /* YL_OP_DWPW: depthwise kernel size (3); otherwise 0 */
+  int64_t w_off;     /* float offset of the GEMM/stencil weights in the blob */
+  int64_t b_off;     /* float offset of the bias (cout floats), or -1 */
+  int64_t w2_off;    /* YL_OP_DWPW: float offset of depthwise weights [k2*k2][cin]; otherwise -1 */
+  int64_t reserved;
+} yl_op;
+
+/* Build an engine on `device` from a layer program and a HOST weight blob.
+ * Replaces: tools/infer.py:34-102 build_model_from_meta + load_state_dict + model.to(device).eval().  */
+int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, size_t blob_floats,
+                     int32_t n_buffers, int32_t n_levels, int32_t device, yl_engine** out);
+int yl_engine_destroy(yl_engine* e);
+
+/* Shapes of the output levels for an input of B x 3 x H x W: shapes[l*4 + {0,1,2,3}] = A, S_h, S_w, 5+C.
+ * Also (re)sizes the activation arena.  Replaces nothing 1:1; the reference gets shapes from the tensors
+ * model.forward returns (model_v2.py:352-377).                                                          */
+int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shapes /* n_levels*4 */);
+
+/* model.forward(x) (scripts/model/model_v2.py:352-377; callers tools/infer.py:456,
+ * scripts/helpers/evaluate.py:273,290,423).  x: [B,3,H,W] fp32 NCHW, normalised.  level_out[l]: caller-
+ * allocated [B,A,S,S,5+C] fp32 contiguous, channel order (tx,ty,tw,th,obj,cls0..).  x is not modified.  */
+int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
+               void* stream);
+
+/* Same as yl_forward but brackets every op with CUDA events on `stream` and returns the device time of each
+ * op in milliseconds (op_ms[n_ops]); synchronises the stream.  Used by bench.py for the per-kernel roofline. */
+int yl_forward_profile(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
+                       void* stream, float* op_ms /* host, n_ops */, int32_t n_ops);
+
+/* Debug/parity tap: copy activation buffer `buf` ([B,H,W,C] NHWC fp32) of the last yl_forward into `dst`
+ * (device).  dims receives H, W, C.  dst may be NULL to query dims only.                                */
+int yl_engine_read_buffer(yl_engine* e, int32_t buf, float* dst, int32_t* dims /*3*/, void* stream);
+
+/* ---- postprocess --------------------------------------------------------------------------------
+ * One fused kernel per batch: sigmoid, anchor-free decode, score threshold, class-wise NMS.
+ * Replaces: scripts/helpers/utils_ms.py:25-123 decode_preds_anchorfree (center_mode "v8", wh_mode
+ * "softplus"), tools/infer.py:466-493 (score = sigmoid(obj)*max sigmoid(cls); C==1 -> obj only; strict
+ * score > conf; per-class torchvision.ops.nms, keep[:max_det] per class via tools/infer.py:134-152), and
+ * with max_det_per_class = 0 (unlimited), conf 0.001, iou 0.65 the evaluation variant
+ * scripts/helpers/helpers.py:86-153.
+ *
+ * level_logits[l]: [B, A_l, Sh_l, Sw_l, D] fp32 (D = 5 + C).  level_dims[l*3 + {0,1,2}] = A_l, Sh_l, Sw_l.
+ * Outputs (capacity `cap` detections per image, caller-allocated, device):
+ *   boxes [B,cap,4] f32 xyxy px in the img_size square, scores [B,cap] f32, classes [B,cap] i64,
+ *   anchor_idx [B,cap] i64 (flat index n = level offset + a*S*S + y*S + x, the reference's N axis),
+ *   counts [B] i32 (= min(K, cap); bit 30 set in counts[b] if K > cap).
+ * Order within an image: class ascending, then score descending, ties by anchor index -- exactly the
+ * concatenation order of tools/infer.py:477-488.
+ * `scratch` is device memory of yl_postprocess_scratch_bytes(B, N) bytes, reusable across calls.       */
+size_t yl_postprocess_scratch_bytes(int32_t B, int64_t n_anchors_total);
+int yl_postprocess(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels,
+                   int32_t B, int32_t D, int32_t img_size, float conf, double iou,
+                   int32_t max_det_per_class, int32_t cap,
+                   float* boxes, float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts,
+                   void* scratch, size_t scratch_bytes, void* stream);
+
+/* Decode only (utils_ms.py:25-123): box [B,N,4], obj [B,N,1], cls [B,N,C] -- obj/cls are raw logits.   */
+int yl_decode(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels, int32_t B,
+              int32_t D, int32_t img_size, float* box, float* obj, float* cls, void* stream);
+
+/* ---- preprocess / back-map (tools/infer.py:121-131,432-453,507-516) --------------------------------
+ * src: uint8 HWC BGR image on the device (h0 x w0 x 3, row pitch `pitch` bytes).  Writes one image of
+ * the batch: dst [3,S,S] fp32 = letterbox(114 pad, bilinear as cv2.INTER_LINEAR) -> RGB -> /255 ->
+ * (x-mean)/std -> CHW.  nh,nw,left,top as computed by the host (int(round()) sizing).                  */
+int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t pitch, float* dst, int32_t S,
+                  int32_t nh, int32_t nw, int32_t left, int32_t top, void* stream);
+
+const char* yl_last_error(void);
+int yl_abi_version(void);
+int yl_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLOLITE_B200_H */

@@ -1,0 +1,93 @@
+"""Parity of the CUDA forward (through the C ABI) against the oracle and the reference-generated golden vectors.
+
+Tolerance: 1e-3 absolute on logits (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FWD_CASES, case_ckpt, golden, synth_ckpt
+from oracle import model_ref
+
+pytestmark = pytest.mark.gpu
+LOGIT_TOL = 1e-3
+
+
+def _engine(ckpt, **kw):
+    import yololite_b200 as y
+    return y.YoloLiteB200(ckpt["state_dict"], ckpt["meta"], device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+@pytest.mark.parametrize("fuse", [True, False])
+def test_forward_matches_golden_and_oracle(name, fuse):
+    ckpt, k = case_ckpt(name)
+    g = golden(name + ".npz")
+    x = model_ref.synth_input(k["B"], k["img"], seed=k["input_seed"])
+    eng = _engine(ckpt, fuse_dwpw=fuse)
+    outs = eng(x.cuda())
+    torch.cuda.synchronize()
+    want = model_ref.forward_ref(ckpt["state_dict"], ckpt["meta"], x)
+    assert [list(o.shape) for o in outs] == g["shapes"].tolist()
+    assert eng.get_strides() == g["strides"].tolist()
+    step = int(g["step"])
+    for i, (o, w) in enumerate(zip(outs, want)):
+        assert o.is_contiguous() and o.dtype == torch.float32
+        err = float((o.cpu() - w).abs().max())
+        assert err <= LOGIT_TOL, (name, i, err)
+        f = o.cpu().reshape(k["B"], -1, o.shape[-1]).numpy()
+        np.testing.assert_allclose(f[:, ::step], g[f"level{i}"], rtol=0, atol=LOGIT_TOL)
+
+
+def test_intermediate_taps_match_oracle():
+    ckpt, k = case_ckpt("fwd_edge_n_64_nc3")
+    x = model_ref.synth_input(2, 64, seed=5)
+    eng = _engine(ckpt, fuse_dwpw=False, reuse_buffers=False)
+    eng(x.cuda())
+    _, feats = model_ref.forward_ref(ckpt["state_dict"], ckpt["meta"], x, return_feats=True)
+    for name in ("c3", "c4", "c5", "p5", "p4", "p3"):
+        got = eng.read_buffer(name, 2).permute(0, 3, 1, 2).cpu()
+        assert got.shape == feats[name].shape
+        assert float((got - feats[name]).abs().max()) <= 2e-4, name
+
+
+def test_edge_n_640_batch_and_batch_invariance():
+    ck = synth_ckpt("edge_n", 80, 640)
+    eng = _engine(ck)
+    x = model_ref.synth_input(3, 640, seed=1)
+    outs = eng(x.cuda())
+    assert [tuple(o.shape) for o in outs] == [(3, 1, 80, 80, 85), (3, 1, 40, 40, 85), (3, 1, 20, 20, 85)]
+    want = model_ref.forward_ref(ck["state_dict"], ck["meta"], x[1:2])
+    single = eng(x[1:2].cuda())
+    for o, s, w in zip(outs, single, want):
+        assert torch.equal(o[1:2], s)                          # an image's logits do not depend on its batch
+        assert float((s.cpu() - w).abs().max()) <= LOGIT_TOL
+    again = eng(x.cuda())
+    for a, b in zip(outs, again):
+        assert torch.equal(a, b)                               # deterministic
+
+
+def test_non_multiple_of_32_input_and_export_concat():
+    ck = synth_ckpt("edge_n", 3, 64)
+    eng = _engine(ck)
+    x = model_ref.synth_input(1, 112, seed=2)[:, :, :104, :88].contiguous()      # 104x88 -> 13x11, 7x6, 4x3
+    want = model_ref.forward_ref(ck["state_dict"], ck["meta"], x)
+    outs = eng(x.cuda())
+    for o, w in zip(outs, want):
+        assert o.shape == w.shape
+        assert float((o.cpu() - w).abs().max()) <= LOGIT_TOL
+    eng.export_concat = True
+    cat = eng(x.cuda())
+    assert cat.shape == (1, sum(w.shape[2] * w.shape[3] for w in want), 8)
+
+
+def test_input_validation_mirrors_reference_errors():
+    ck = synth_ckpt("edge_n", 3, 64)
+    eng = _engine(ck)
+    with pytest.raises(ValueError):
+        eng(torch.zeros(1, 3, 64, 64))                 # CPU tensor: no CPU path
+    with pytest.raises(ValueError):
+        eng(torch.zeros(1, 4, 64, 64, device="cuda"))
+    x = torch.randn(1, 3, 64, 64, device="cuda")
+    x0 = x.clone()
+    eng(x)
+    assert torch.equal(x, x0)                          # input not modified

@@ -1,0 +1,86 @@
+"""Host-side lowering (BN folding, weight layouts, op wiring, buffer reuse) checked on CPU: the op program,
+executed by a plain-torch interpreter of the documented op semantics, must reproduce the oracle forward."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import FWD_CASES, case_ckpt
+from oracle import model_ref
+from program_interp import run_program
+from yololite_b200 import packer
+
+
+@pytest.mark.parametrize("name", FWD_CASES)
+@pytest.mark.parametrize("fuse,reuse", [(True, True), (False, False)])
+def test_program_reproduces_oracle(name, fuse, reuse):
+    ckpt, k = case_ckpt(name)
+    P = packer.lower(ckpt["state_dict"], ckpt["meta"], fuse_dwpw=fuse, reuse_buffers=reuse)
+    x = model_ref.synth_input(k["B"], k["img"], seed=k["input_seed"])
+    want = model_ref.forward_ref(ckpt["state_dict"], ckpt["meta"], x)
+    got = run_program(P, x)
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert float((a - b).abs().max()) < 2e-4
+    assert P.strides == model_ref.strides_ref(ckpt["meta"])
+
+
+def test_every_checkpoint_tensor_is_consumed_or_known_unused():
+    ckpt, _ = case_ckpt("fwd_edge_n_64_nc3")
+    sd = packer._SD(ckpt["state_dict"])
+    orig = packer._SD
+    try:
+        packer._SD = lambda _: sd
+        packer.lower(ckpt["state_dict"], ckpt["meta"])
+    finally:
+        packer._SD = orig
+    unused = set(ckpt["state_dict"]) - sd.used
+    # model_v2.py:297-300: the P6 branch parameters exist in every state_dict even when use_p6 is False
+    assert all(k.startswith(("p6_down", "p6_bn", "smooth6")) for k in unused), sorted(unused)[:5]
+
+
+def test_buffer_reuse_never_aliases_live_tensors():
+    ckpt, _ = case_ckpt("fwd_edge_n_96_p2p6_a2")
+    P = packer.lower(ckpt["state_dict"], ckpt["meta"], reuse_buffers=True)
+    Pn = packer.lower(ckpt["state_dict"], ckpt["meta"], reuse_buffers=False)
+    assert P.n_buffers < Pn.n_buffers
+    for op in P.ops:
+        ins = {op[f] for f in ("src", "res", "up") if op[f] >= 0}
+        assert op["dst"] not in ins
+    # blob arrays are 16-byte aligned, as the kernels' float4 loads require
+    for op in P.ops:
+        assert op["w_off"] % 4 == 0 and (op["b_off"] < 0 or op["b_off"] % 4 == 0) and (op["w2_off"] < 0 or op["w2_off"] % 4 == 0)
+
+
+def test_parse_meta_mirrors_reference_errors():
+    meta = model_ref.make_meta("edge_n", 3, 64)
+    cfg = packer.parse_meta(meta)
+    assert (cfg.fpn_channels, cfg.depth, cfg.head_depth, cfg.anchors) == (96, 1, 1, (1, 1, 1))
+    m = packer.parse_meta(model_ref.make_meta("edge_m", 3, 64))
+    assert (m.fpn_channels, m.depth, m.head_depth) == (244, 2, 2)
+    bad = dict(meta); bad["arch"] = "resnet"
+    with pytest.raises(ValueError):
+        packer.parse_meta(bad)
+    bad = dict(meta); bad["config"] = {"model": meta["config"]["model"], "training": {}}
+    with pytest.raises(KeyError):
+        packer.parse_meta(bad)      # tools/infer.py:49-50 hard-indexes use_p6/use_p2
+    bad = dict(meta); bad["backbone"] = "hgnetv2_b0"
+    with pytest.raises(ValueError):
+        packer.parse_meta(bad)
+
+
+def test_product_synth_checkpoint_matches_reference_state_dict_spec():
+    from yololite_b200 import synth
+    for mdl, kw in (("edge_n", {}), ("edge_m", {}), ("edge_n", dict(use_p2=True, use_p6=True, anchors=2))):
+        meta = synth.make_meta(mdl, 5, 64, **kw)
+        mine = synth.state_shapes(meta)
+        spec = model_ref.state_spec(model_ref.make_meta(mdl, 5, 64, **kw))
+        assert set(mine) == set(spec)
+        for k, shp in mine.items():
+            assert tuple(shp) == tuple(spec[k][0]), k
+    ck = synth.random_checkpoint(synth.make_meta("edge_n", 4, 64), seed=0, obj_bias=-1.0)
+    x = model_ref.synth_input(1, 64, seed=0)
+    outs = run_program(packer.lower(ck["state_dict"], ck["meta"]), x)
+    want = model_ref.forward_ref(ck["state_dict"], ck["meta"], x)
+    for a, b in zip(outs, want):
+        assert torch.isfinite(a).all() and float((a - b).abs().max()) < 2e-4

@@ -1,0 +1,233 @@
+// C ABI + layer-program executor (see include/yololite_b200.h).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace yl {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+struct BufShape {
+  int H = 0, W = 0, C = 0;
+  size_t off = 0, bytes = 0;
+};
+
+}  // namespace yl
+
+struct yl_engine {
+  int device = 0;
+  std::vector<yl_op> ops;
+  float* d_blob = nullptr;
+  size_t blob_floats = 0;
+  int n_buffers = 0, n_levels = 0;
+  // plan
+  int B = 0, H = 0, W = 0;
+  std::vector<yl::BufShape> bufs;
+  std::vector<int> level_shape;  // n_levels * 4
+  std::vector<int> op_hout, op_wout, op_hin, op_win, op_hu, op_wu;
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+};
+
+namespace yl {
+
+static int plan(yl_engine* e, int B, int H, int W) {
+  if (e->B == B && e->H == H && e->W == W && e->arena) return 0;
+  YL_REQUIRE(B >= 1 && H >= 1 && W >= 1, "B,H,W must be positive");
+  const int nops = (int)e->ops.size();
+  std::vector<BufShape> bufs(e->n_buffers);
+  std::vector<int> lvl(e->n_levels * 4, 0);
+  e->op_hout.assign(nops, 0); e->op_wout.assign(nops, 0); e->op_hin.assign(nops, 0); e->op_win.assign(nops, 0);
+  e->op_hu.assign(nops, 0); e->op_wu.assign(nops, 0);
+  for (int i = 0; i < nops; ++i) {
+    const yl_op& op = e->ops[i];
+    int hin, win, cin;
+    if (op.src == YL_SRC_INPUT) { hin = H; win = W; cin = 3; }
+    else {
+      YL_REQUIRE(op.src >= 0 && op.src < e->n_buffers, "op.src out of range");
+      hin = bufs[op.src].H; win = bufs[op.src].W; cin = bufs[op.src].C;
+      YL_REQUIRE(hin > 0, "op reads a buffer that was never written");
+    }
+    YL_REQUIRE(cin == op.cin, "op.cin does not match the source buffer");
+    const int pad = op.k / 2;
+    const int hout = (hin + 2 * pad - op.k) / op.stride + 1;
+    const int wout = (win + 2 * pad - op.k) / op.stride + 1;
+    YL_REQUIRE(hout >= 1 && wout >= 1, "input too small for the network");
+    e->op_hin[i] = hin; e->op_win[i] = win; e->op_hout[i] = hout; e->op_wout[i] = wout;
+    if (op.dst >= 0) {
+      YL_REQUIRE(op.dst < e->n_buffers, "op.dst out of range");
+      BufShape& d = bufs[op.dst];
+      d.H = hout; d.W = wout; d.C = op.cout;
+      d.bytes = std::max(d.bytes, (size_t)B * hout * wout * op.cout * sizeof(float));
+    } else {
+      const int l = -op.dst - 1;
+      YL_REQUIRE(l < e->n_levels && op.anchors >= 1 && op.cout % op.anchors == 0, "bad level output op");
+      lvl[l * 4 + 0] = op.anchors; lvl[l * 4 + 1] = hout; lvl[l * 4 + 2] = wout; lvl[l * 4 + 3] = op.cout / op.anchors;
+    }
+    if (op.res >= 0) {
+      YL_REQUIRE(op.res < e->n_buffers && bufs[op.res].H == hout && bufs[op.res].W == wout && bufs[op.res].C == op.cout,
+                 "residual shape mismatch");
+    }
+    if (op.up >= 0) {
+      YL_REQUIRE(op.up < e->n_buffers && bufs[op.up].C == op.cout && bufs[op.up].H > 0, "upsample source mismatch");
+      e->op_hu[i] = bufs[op.up].H; e->op_wu[i] = bufs[op.up].W;
+    }
+  }
+  size_t off = 0;
+  for (auto& b : bufs) { b.off = off; off += (b.bytes + 255) / 256 * 256; }
+  if (off > e->arena_bytes) {
+    if (e->arena) YL_CHECK_CUDA(cudaFree(e->arena));
+    e->arena = nullptr; e->arena_bytes = 0;
+    YL_CHECK_CUDA(cudaMalloc(&e->arena, off));
+    e->arena_bytes = off;
+  }
+  e->bufs = bufs; e->level_shape = lvl; e->B = B; e->H = H; e->W = W;
+  return 0;
+}
+
+}  // namespace yl
+
+extern "C" {
+
+const char* yl_last_error(void) { return yl::g_err.c_str(); }
+int yl_abi_version(void) { return YL_ABI_VERSION; }
+int yl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, size_t blob_floats, int32_t n_buffers,
+                     int32_t n_levels, int32_t device, yl_engine** out) {
+  using namespace yl;
+  YL_REQUIRE(ops && n_ops > 0 && blob_host && blob_floats > 0 && out, "null/empty arguments");
+  YL_REQUIRE(n_buffers >= 1 && n_levels >= 1 && n_levels <= 8, "n_buffers >= 1, 1 <= n_levels <= 8");
+  int ndev = 0;
+  YL_CHECK_CUDA(cudaGetDeviceCount(&ndev));
+  YL_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU fallback)");
+  YL_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  YL_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  YL_REQUIRE(prop.major == 10, "yololite_b200 is built for sm_100a (B200) only");
+  for (int i = 0; i < n_ops; ++i) {
+    const yl_op& op = ops[i];
+    YL_REQUIRE(op.kind >= YL_OP_STEM && op.kind <= YL_OP_DWPW, "unknown op kind");
+    YL_REQUIRE(op.k >= 1 && (op.k & 1) && op.stride >= 1 && op.cin >= 1 && op.cout >= 1, "bad conv geometry");
+    YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
+    YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
+    YL_REQUIRE((op.w_off & 3) == 0 && (op.b_off < 0 || (op.b_off & 3) == 0), "blob offsets must be 16-byte aligned");
+  }
+  yl_engine* e = new yl_engine();
+  e->device = device;
+  e->ops.assign(ops, ops + n_ops);
+  e->n_buffers = n_buffers; e->n_levels = n_levels; e->blob_floats = blob_floats;
+  if (cudaMalloc(&e->d_blob, blob_floats * sizeof(float)) != cudaSuccess ||
+      cudaMemcpy(e->d_blob, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("weight upload failed: ") + cudaGetErrorString(cudaGetLastError()));
+    if (e->d_blob) cudaFree(e->d_blob);
+    delete e;
+    return -2;
+  }
+  *out = e;
+  return 0;
+}
+
+int yl_engine_destroy(yl_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  if (e->arena) cudaFree(e->arena);
+  if (e->d_blob) cudaFree(e->d_blob);
+  delete e;
+  return 0;
+}
+
+int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shapes) {
+  using namespace yl;
+  YL_REQUIRE(e, "null engine");
+  YL_CHECK_CUDA(cudaSetDevice(e->device));
+  if (int rc = plan(e, B, H, W)) return rc;
+  if (shapes) std::memcpy(shapes, e->level_shape.data(), e->level_shape.size() * sizeof(int));
+  return 0;
+}
+
+static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
+                        void* stream, cudaEvent_t* ev) {
+  using namespace yl;
+  YL_REQUIRE(e && x && level_out, "null argument");
+  YL_CHECK_CUDA(cudaSetDevice(e->device));
+  if (int rc = plan(e, B, H, W)) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  auto bufptr = [&](int id) -> float* { return reinterpret_cast<float*>(e->arena + e->bufs[id].off); };
+  for (size_t i = 0; i < e->ops.size(); ++i) {
+    const yl_op& op = e->ops[i];
+    ConvParams p{};
+    p.in = op.src == YL_SRC_INPUT ? x : bufptr(op.src);
+    p.w = e->d_blob + op.w_off;
+    p.bias = op.b_off >= 0 ? e->d_blob + op.b_off : nullptr;
+    p.res = op.res >= 0 ? bufptr(op.res) : nullptr;
+    p.up = op.up >= 0 ? bufptr(op.up) : nullptr;
+    p.w2 = op.w2_off >= 0 ? e->d_blob + op.w2_off : nullptr;
+    if (op.dst >= 0) p.out = bufptr(op.dst);
+    else {
+      p.out = level_out[-op.dst - 1];
+      YL_REQUIRE(p.out, "null level output pointer");
+    }
+    p.B = B; p.Hin = e->op_hin[i]; p.Win = e->op_win[i]; p.Cin = op.cin;
+    p.Hout = e->op_hout[i]; p.Wout = e->op_wout[i]; p.Cout = op.cout;
+    p.KS = op.k; p.stride = op.stride; p.pad = op.k / 2;
+    p.Hu = e->op_hu[i]; p.Wu = e->op_wu[i];
+    p.act = op.act; p.anchors = op.anchors;
+    int rc = 0;
+    switch (op.kind) {
+      case YL_OP_STEM: rc = launch_stem(p, st); break;
+      case YL_OP_CONV: rc = launch_conv_gemm(p, st); break;
+      case YL_OP_DW: rc = launch_dw(p, st); break;
+      case YL_OP_DWPW: p.KS = op.k2; p.pad = op.k2 / 2; rc = launch_dwpw(p, st); break;
+      default: YL_REQUIRE(false, "unknown op kind");
+    }
+    if (rc) return rc;
+    if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
+  }
+  return 0;
+}
+
+int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out, void* stream) {
+  return forward_impl(e, x, B, H, W, level_out, stream, nullptr);
+}
+
+int yl_forward_profile(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
+                       void* stream, float* op_ms, int32_t n_ops) {
+  using namespace yl;
+  YL_REQUIRE(e && op_ms && n_ops == (int)e->ops.size(), "op_ms must hold one float per op");
+  YL_CHECK_CUDA(cudaSetDevice(e->device));
+  std::vector<cudaEvent_t> ev(n_ops + 1);
+  for (auto& v : ev) YL_CHECK_CUDA(cudaEventCreate(&v));
+  int rc = forward_impl(e, x, B, H, W, level_out, stream, ev.data());
+  if (rc == 0) {
+    if (cudaEventSynchronize(ev[n_ops]) != cudaSuccess) { set_error("event sync failed"); rc = -2; }
+    for (int i = 0; i < n_ops && rc == 0; ++i)
+      if (cudaEventElapsedTime(&op_ms[i], ev[i], ev[i + 1]) != cudaSuccess) { set_error("elapsed time failed"); rc = -2; }
+  }
+  for (auto& v : ev) cudaEventDestroy(v);
+  return rc;
+}
+
+int yl_engine_read_buffer(yl_engine* e, int32_t buf, float* dst, int32_t* dims, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(e && e->arena, "engine has no plan yet (call yl_forward first)");
+  YL_REQUIRE(buf >= 0 && buf < e->n_buffers, "buffer id out of range");
+  const BufShape& b = e->bufs[buf];
+  if (dims) { dims[0] = b.H; dims[1] = b.W; dims[2] = b.C; }
+  if (dst) {
+    YL_CHECK_CUDA(cudaMemcpyAsync(dst, e->arena + b.off, (size_t)e->B * b.H * b.W * b.C * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
+  }
+  return 0;
+}
+
+}  // extern "C"

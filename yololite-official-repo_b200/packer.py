@@ -1,0 +1,337 @@
+"""Lower a reference checkpoint {"state_dict", "meta"} into the engine's layer program.
+
+Reads the same files the reference reads:
+  * meta layout                    tools/train.py:62-75 (save_checkpoint_state), tools/infer.py:34-77
+  * FPN / head module tree         scripts/model/model_v2.py:250-377 (YOLOLiteMS_CPU), :77-224 (YOLOLiteMS)
+  * backbone                       timm `mobilenetv4_conv_small[_050]` as called at model_v2.py:266-272; block
+                                   structure as dumped at YoloLite_custom_training.ipynb:392-850
+
+and emits (a) a flat op list over numbered NHWC activation buffers, (b) one fp32 blob with BatchNorm folded
+into the preceding conv (done in float64, rounded once), GEMM weights stored [K][N] with N padded to 4.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+BN_EPS = 1e-5
+
+# ("cn", k, stride, c) | ("uir", dw_start_k, dw_mid_k, stride, expand, c)
+_MNV4_SMALL = (
+    (("cn", 3, 2, 32), ("cn", 1, 1, 32)),
+    (("cn", 3, 2, 96), ("cn", 1, 1, 64)),
+    (("uir", 5, 5, 2, 3.0, 96),) + (("uir", 0, 3, 1, 2.0, 96),) * 4 + (("uir", 3, 0, 1, 4.0, 96),),
+    (("uir", 3, 3, 2, 6.0, 128), ("uir", 5, 5, 1, 4.0, 128), ("uir", 0, 5, 1, 4.0, 128),
+     ("uir", 0, 5, 1, 3.0, 128), ("uir", 0, 3, 1, 4.0, 128), ("uir", 0, 3, 1, 4.0, 128)),
+    (("cn", 1, 1, 960),),
+)
+BACKBONES = {"mobilenetv4_conv_small": (_MNV4_SMALL, 1.0, 32), "mobilenetv4_conv_small_050": (_MNV4_SMALL, 0.5, 32)}
+
+
+def _round_ch(v: float, div: int = 8) -> int:
+    n = max(div, int(v + div / 2) // div * div)
+    return n + div if n < 0.9 * v else n
+
+
+@dataclass
+class ModelCfg:
+    arch: str
+    backbone: str
+    num_classes: int
+    fpn_channels: int
+    depth: int
+    head_depth: int
+    use_p6: bool
+    use_p2: bool
+    img_size: int
+    levels: Tuple[str, ...]
+    anchors: Tuple[int, ...]
+    names: List[str]
+
+
+def parse_meta(meta: dict) -> ModelCfg:
+    """Same field resolution (and the same KeyError / ValueError behaviour) as tools/infer.py:34-77."""
+    cfg = meta.get("config", {}) or {}
+    mcfg = cfg.get("model", {}) or {}
+    tcfg = cfg.get("training", {}) or {}
+    arch = (meta.get("arch") or mcfg.get("arch") or "YOLOLiteMS").lower()
+    backbone = meta.get("backbone") or mcfg.get("backbone") or "resnet18"
+    nc = int(meta.get("num_classes") or mcfg.get("num_classes") or 80)
+    apl = tuple(meta.get("num_anchors_per_level") or (1, 1, 1))
+    use_p6 = cfg["training"]["use_p6"]
+    use_p2 = cfg["training"]["use_p2"]
+    if arch not in ("yololitems", "yololitems_cpu"):
+        raise ValueError(f"Okänd arch i meta/config: {arch}")
+    if backbone not in BACKBONES:
+        raise ValueError(f"backbone {backbone!r} has no sm_100a lowering yet (supported: {sorted(BACKBONES)})")
+    levels = (("p2",) if use_p2 else ()) + ("p3", "p4", "p5") + (("p6",) if use_p6 else ())
+    if len(apl) >= 3:
+        a3, a4, a5 = (int(v) for v in apl[:3])
+        amap = {"p2": a3, "p3": a3, "p4": a4, "p5": a5, "p6": a5}
+    else:
+        a = int(apl[0]) if len(apl) else 1
+        amap = dict.fromkeys(("p2", "p3", "p4", "p5", "p6"), a)
+    names = meta.get("names") or [str(i) for i in range(int(meta.get("num_classes", 80)))]
+    return ModelCfg(arch=arch, backbone=backbone, num_classes=nc,
+                    fpn_channels=int(int(mcfg.get("fpn_channels", 128)) * float(mcfg.get("width_multiple", 1.0))),
+                    depth=max(1, round(2 * float(mcfg.get("depth_multiple", 1.0)))),
+                    head_depth=int(mcfg.get("head_depth", 1)), use_p6=bool(use_p6), use_p2=bool(use_p2),
+                    img_size=int(tcfg.get("img_size", meta.get("img_size", 640))), levels=levels,
+                    anchors=tuple(amap[l] for l in levels), names=list(names))
+
+
+@dataclass
+class _T:
+    """A virtual activation tensor."""
+    vid: int
+    C: int
+    red: int            # reduction w.r.t. the network input (bookkeeping only)
+
+
+@dataclass
+class Program:
+    ops: List[dict] = field(default_factory=list)
+    blob: List[np.ndarray] = field(default_factory=list)
+    blob_len: int = 0
+    n_virtual: int = 0
+    taps: Dict[str, int] = field(default_factory=dict)    # name -> virtual tensor id (debug/parity taps)
+    strides: List[int] = field(default_factory=list)
+    cfg: Optional[ModelCfg] = None
+    n_buffers: int = 0
+    vmap: Dict[int, int] = field(default_factory=dict)    # virtual id -> physical buffer id
+
+    def add_blob(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+        off = self.blob_len
+        pad = (-arr.size) % 64                        # keep every array 256-byte aligned
+        self.blob.append(arr)
+        if pad:
+            self.blob.append(np.zeros(pad, np.float32))
+        self.blob_len += arr.size + pad
+        return off
+
+    def new(self, C: int, red: int) -> _T:
+        t = _T(self.n_virtual, C, red)
+        self.n_virtual += 1
+        return t
+
+
+class _SD:
+    def __init__(self, sd):
+        self.sd = sd
+        self.used = set()
+
+    def get(self, key) -> np.ndarray:
+        if key not in self.sd:
+            raise KeyError(f"checkpoint state_dict has no {key!r}")
+        self.used.add(key)
+        v = self.sd[key]
+        return (v.detach().cpu().double().numpy() if isinstance(v, torch.Tensor) else np.asarray(v, np.float64))
+
+    def bn(self, prefix) -> Tuple[np.ndarray, np.ndarray]:
+        g, b = self.get(prefix + ".weight"), self.get(prefix + ".bias")
+        m, v = self.get(prefix + ".running_mean"), self.get(prefix + ".running_var")
+        self.used.add(prefix + ".num_batches_tracked")
+        s = g / np.sqrt(v + BN_EPS)
+        return s, b - m * s
+
+
+def _gemm_w(w: np.ndarray) -> np.ndarray:
+    """[Cout,Cin,k,k] -> [k*k*Cin][Cout padded to 4], k index = (ky*k+kx)*Cin+ci."""
+    cout = w.shape[0]
+    m = np.transpose(w, (2, 3, 1, 0)).reshape(-1, cout)
+    ld = (cout + 3) // 4 * 4
+    out = np.zeros((m.shape[0], ld), np.float64)
+    out[:, :cout] = m
+    return out
+
+
+def _pad4(b: np.ndarray) -> np.ndarray:
+    out = np.zeros(((b.size + 3) // 4 * 4,), np.float64)
+    out[:b.size] = b
+    return out
+
+
+def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True) -> Program:
+    cfg = parse_meta(meta)
+    sd = _SD(state_dict)
+    P = Program(cfg=cfg)
+
+    def emit(kind, src: Optional[_T], cout, red, k=1, stride=1, act=L.ACT_NONE, w=None, b=None, res: Optional[_T] = None,
+             up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0) -> Optional[_T]:
+        dst = None if level is not None else P.new(cout, red)
+        P.ops.append(dict(kind=kind, src=(-1 if src is None else src.vid), dst=(-(1 + level) if level is not None else dst.vid),
+                          res=(-1 if res is None else res.vid), up=(-1 if up is None else up.vid),
+                          cin=(3 if src is None else src.C), cout=cout, k=k, stride=stride, act=act, anchors=anchors, k2=k2,
+                          w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
+                          w2_off=(-1 if w2 is None else P.add_blob(w2))))
+        return dst
+
+    def conv_bn(x: Optional[_T], wkey, bnkey, k, stride, act, red, res=None) -> _T:
+        w = sd.get(wkey + ".weight")
+        s, b = sd.bn(bnkey)
+        w = w * s[:, None, None, None]
+        cout = w.shape[0]
+        if x is None:      # stem on the NCHW input: [k*k*3][Cout]
+            return emit(L.OP_STEM, None, cout, red, k=k, stride=stride, act=act,
+                        w=np.transpose(w, (2, 3, 1, 0)).reshape(-1, cout), b=b)
+        return emit(L.OP_CONV, x, cout, red, k=k, stride=stride, act=act, w=_gemm_w(w), b=b, res=res)
+
+    def dw_bn(x: _T, wkey, bnkey, k, stride, act, red) -> _T:
+        w = sd.get(wkey + ".weight")                       # [C,1,k,k]
+        s, b = sd.bn(bnkey)
+        w = w * s[:, None, None, None]
+        return emit(L.OP_DW, x, x.C, red, k=k, stride=stride, act=act, w=np.transpose(w, (2, 3, 1, 0)).reshape(k * k, -1), b=b)
+
+    # ---------------- backbone
+    table, mult, stem_c = BACKBONES[cfg.backbone]
+    bb = "backbone."
+    x = conv_bn(None, bb + "conv_stem", bb + "bn1", 3, 2, L.ACT_RELU, 2)
+    feats = [x]
+    red = 2
+    for si, stage in enumerate(table):
+        for bi, spec in enumerate(stage):
+            key = f"{bb}blocks.{si}.{bi}"
+            if spec[0] == "cn":
+                _, k, s, c = spec
+                red *= s
+                x = conv_bn(x, key + ".conv", key + ".bn1", k, s, L.ACT_RELU, red)
+            else:
+                _, ks, km, s, e, c = spec
+                cout = _round_ch(c * mult)
+                skip = x if (x.C == cout and s == 1) else None
+                y = x
+                if ks:
+                    y = dw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, 1 if km else s, L.ACT_NONE,
+                              red * (1 if km else s))
+                y = conv_bn(y, key + ".pw_exp.conv", key + ".pw_exp.bn", 1, 1, L.ACT_RELU, y.red)
+                if km:
+                    y = dw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, s, L.ACT_RELU, red * s)
+                red *= s
+                x = conv_bn(y, key + ".pw_proj.conv", key + ".pw_proj.bn", 1, 1, L.ACT_NONE, red, res=skip)
+            last_of_stage = bi == len(stage) - 1
+            nxt = table[si + 1][0] if si + 1 < len(table) else None
+            nxt_stride = None if nxt is None else (nxt[2] if nxt[0] == "cn" else nxt[3])
+            if last_of_stage and (nxt is None or nxt_stride > 1):
+                feats.append(x)
+    take = 4 if cfg.use_p2 else 3
+    feats = feats[-take:]
+    P.strides = [f.red for f in feats] + ([feats[-1].red * 2] if cfg.use_p6 else [])
+
+    # ---------------- FPN
+    Fc, d, C = cfg.fpn_channels, cfg.depth, cfg.num_classes
+    cpu = cfg.arch == "yololitems_cpu"
+
+    def dw_block(x: _T, name: str, n: int) -> _T:           # model_v2.py:23-39
+        for i in range(n):
+            wd = sd.get(f"{name}.block.{4*i}.weight")        # [C,1,3,3], no BN, no act
+            wp = sd.get(f"{name}.block.{4*i+1}.weight")
+            s, b = sd.bn(f"{name}.block.{4*i+2}")
+            wp = wp * s[:, None, None, None]
+            wd9 = np.transpose(wd, (2, 3, 1, 0)).reshape(9, -1)
+            if fuse_dwpw and x.C <= 384:
+                x = emit(L.OP_DWPW, x, wp.shape[0], x.red, k=1, act=L.ACT_RELU, w=_gemm_w(wp), b=b, w2=wd9, k2=3)
+            else:
+                t = emit(L.OP_DW, x, x.C, x.red, k=3, act=L.ACT_NONE, w=wd9)
+                x = emit(L.OP_CONV, t, wp.shape[0], x.red, k=1, act=L.ACT_RELU, w=_gemm_w(wp), b=b)
+        return x
+
+    def dense_block(x: _T, name: str, n: int) -> _T:        # model_v2.py:15-22
+        for i in range(n):
+            x = conv_bn(x, f"{name}.{3*i}", f"{name}.{3*i+1}", 3, 1, L.ACT_SILU, x.red)
+        return x
+
+    smooth = dw_block if cpu else dense_block
+
+    def lateral(c: _T, name: str, up: Optional[_T]) -> _T:
+        w = sd.get(name + ".weight")
+        return emit(L.OP_CONV, c, w.shape[0], c.red, k=1, w=_gemm_w(w), b=sd.get(name + ".bias"), up=up)
+
+    c5, c4, c3 = feats[-1], feats[-2], feats[-3]
+    pyr: Dict[str, _T] = {}
+    pyr["p5"] = smooth(lateral(c5, "lateral5", None), "smooth5", d)
+    pyr["p4"] = smooth(lateral(c4, "lateral4", pyr["p5"]), "smooth4", d)
+    pyr["p3"] = smooth(lateral(c3, "lateral3", pyr["p4"]), "smooth3", d)
+    if cfg.use_p2:
+        pyr["p2"] = smooth(lateral(feats[0], "lateral2", pyr["p3"]), "smooth2", d)
+    if cfg.use_p6:
+        t = conv_bn(pyr["p5"], "p6_down", "p6_bn", 3, 2, L.ACT_RELU if cpu else L.ACT_SILU, pyr["p5"].red * 2)
+        pyr["p6"] = smooth(t, "smooth6", d)
+    P.taps.update({"c3": c3.vid, "c4": c4.vid, "c5": c5.vid, **{k: v.vid for k, v in pyr.items()}})
+
+    # ---------------- heads (model_v2.py:42-53, :340-350): one GEMM with N = A*(5+C), rows ordered a*(5+C)+d
+    for li, (lvl, A) in enumerate(zip(cfg.levels, cfg.anchors)):
+        name = "head" + lvl[1]
+        p = pyr[lvl]
+        for i in range(cfg.head_depth):
+            p = dw_block(p, f"{name}.trunk.{i}", 1)
+        wb, bb_ = sd.get(f"{name}.out.box.weight")[:, :, 0, 0], sd.get(f"{name}.out.box.bias")
+        wo, bo = sd.get(f"{name}.out.obj.weight")[:, :, 0, 0], sd.get(f"{name}.out.obj.bias")
+        wc, bc = sd.get(f"{name}.out.cls.weight")[:, :, 0, 0], sd.get(f"{name}.out.cls.bias")
+        D = 5 + C
+        W = np.zeros((A * D, Fc), np.float64)
+        Bv = np.zeros((A * D,), np.float64)
+        for a in range(A):
+            W[a * D:a * D + 4] = wb[a * 4:a * 4 + 4]; Bv[a * D:a * D + 4] = bb_[a * 4:a * 4 + 4]
+            W[a * D + 4] = wo[a]; Bv[a * D + 4] = bo[a]
+            W[a * D + 5:(a + 1) * D] = wc[a * C:(a + 1) * C]; Bv[a * D + 5:(a + 1) * D] = bc[a * C:(a + 1) * C]
+        emit(L.OP_CONV, p, A * D, p.red, k=1, w=_gemm_w(W[:, :, None, None]), b=Bv, anchors=A, level=li)
+
+    _assign_buffers(P, reuse_buffers)
+    return P
+
+
+def _assign_buffers(P: Program, reuse: bool) -> None:
+    """Map virtual tensors to physical buffers; with reuse, a buffer is recycled after its last reader."""
+    last_use: Dict[int, int] = {}
+    for i, op in enumerate(P.ops):
+        for f in ("src", "res", "up"):
+            if op[f] >= 0:
+                last_use[op[f]] = i
+    if not reuse:
+        P.vmap = {v: v for v in range(P.n_virtual)}
+        P.n_buffers = P.n_virtual
+    else:
+        free: List[int] = []
+        vmap: Dict[int, int] = {}
+        n = 0
+        for i, op in enumerate(P.ops):
+            if op["dst"] >= 0:
+                if free:
+                    pid = free.pop()
+                else:
+                    pid = n
+                    n += 1
+                vmap[op["dst"]] = pid
+            # release inputs whose last reader is this op (after allocating dst: never alias in/out)
+            for f in ("src", "res", "up"):
+                v = op[f]
+                if v >= 0 and last_use.get(v) == i and vmap[v] not in free:
+                    free.append(vmap[v])
+            if op["dst"] >= 0 and op["dst"] not in last_use:      # dead tensor
+                free.append(vmap[op["dst"]])
+        P.vmap, P.n_buffers = vmap, max(n, 1)
+    for op in P.ops:
+        for f in ("src", "res", "up", "dst"):
+            if op[f] >= 0:
+                op[f] = P.vmap[op[f]]
+    P.taps = {k: P.vmap[v] for k, v in P.taps.items()}
+
+
+def to_c(P: Program):
+    """(ctypes op array, contiguous fp32 blob)."""
+    arr = (L.YlOp * len(P.ops))()
+    for i, op in enumerate(P.ops):
+        o = arr[i]
+        for f in ("kind", "src", "dst", "res", "up", "cin", "cout", "k", "stride", "act", "anchors", "k2", "w_off", "b_off",
+                  "w2_off"):
+            setattr(o, f, int(op[f]))
+        o.reserved = 0
+    blob = np.concatenate(P.blob).astype(np.float32, copy=False)
+    assert blob.size == P.blob_len
+    return arr, blob
