@@ -439,11 +439,11 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
   const size_t tile_bytes = (size_t)POST_TILE * D * sizeof(float);
   const size_t sort_bytes = (size_t)POST_SMEM_KEYS * 9;
   const size_t smem = (tile_bytes > sort_bytes ? tile_bytes : sort_bytes) + 16;
-  YL_REQUIRE(smem <= 227 * 1024, "5+C too large for the shared-memory tile (C <= 221)");
+  YL_REQUIRE(smem <= 200 * 1024, "5+C too large for the shared-memory tile (C <= 195)");
   static thread_local size_t smem_set = 0;
   if (smem > smem_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-    smem_set = 227 * 1024;
+    YL_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
   }
   const unsigned grid = (unsigned)B * (unsigned)p.tile_off[n_levels];
   post_kernel<<<grid, POST_THREADS, smem, st>>>(p);
