@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tc", action="store_true", help="fp32 SIMT kernels only (A/B against the tcgen05 path)")
+    ap.add_argument("--dump-ops", default="", help="write per-op timings to this JSON file")
     return ap.parse_args()
 
 
@@ -213,7 +215,7 @@ def run_b200(a):
     x = normalise(synth_input_u8(B, S, 1234 + rank, dev))
     obj_bias = calibrate_obj_bias(y, ckpt_fn, x, a)
     ck = ckpt_fn(obj_bias)
-    eng = y.YoloLiteB200(**ck, device=dev)
+    eng = y.YoloLiteB200(**ck, device=dev, tensor_cores=not a.no_tc)
     post = y.PostProcessor()
     shapes = eng.level_shapes(B, S, S)
     outs = [torch.empty((B, A, sh, sw, D), device=dev) for (A, sh, sw, D) in shapes]
@@ -319,6 +321,11 @@ def run_b200(a):
                      "frac_of_per_kernel_traffic_roofline": (sum_bytes / (fwd_ms + post_ms) * 1e3 / 1e9) / peak,
                      "forward_ms": fwd_ms, "post_ms": post_ms}
     top5 = sorted(cand, reverse=True)[:6]
+    if a.dump_ops and rank == 0:
+        with open(a.dump_ops, "w") as f:
+            json.dump([{"i": i, "kind": nm, "cin": op["cin"], "cout": op["cout"], "k": op["k"], "s": op["stride"], "tc": op["wt_off"] >= 0,
+                        "ms": float(t), "MB": nb / 1e6, "GBps": nb / (t / 1e3) / 1e9} for (nm, i, nb, t, op) in per_op] +
+                      [{"i": -1, "kind": "post_kernel", "ms": post_ms}], f, indent=0)
 
     # ---- end to end through the public API with HOST buffers: pinned fp32 input -> H2D -> forward+post -> D2H results
     e2e = None

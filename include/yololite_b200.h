@@ -59,7 +59,8 @@ typedef struct yl_op {
   int64_t w_off;     /* float offset of the GEMM/stencil weights in the blob */
   int64_t b_off;     /* float offset of the bias (cout floats), or -1 */
   int64_t w2_off;    /* YL_OP_DWPW: float offset of depthwise weights [k2*k2][cin]; otherwise -1 */
-  int64_t reserved;
+  int64_t wt_off;    /* float offset of the tcgen05 weight image [2 (hi,lo)][ceil(K/32)][ceil16(cout)][32], pre-split
+                        into TF32 hi/lo and pre-swizzled (SWIZZLE_128B, K-major), or -1 */
 } yl_op;
 
 /* Build an engine on `device` from a layer program and a HOST weight blob.
@@ -67,6 +68,10 @@ typedef struct yl_op {
 int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, size_t blob_floats,
                      int32_t n_buffers, int32_t n_levels, int32_t device, yl_engine** out);
 int yl_engine_destroy(yl_engine* e);
+
+/* Engine options.  key "tensor_cores": 1 (default) = run eligible convs on the tcgen05 3xTF32 kernel, 0 = fp32 SIMT
+ * kernels only.  Unknown keys return an error.                                                          */
+int yl_engine_set_option(yl_engine* e, const char* key, int32_t value);
 
 /* Shapes of the output levels for an input of B x 3 x H x W: shapes[l*4 + {0,1,2,3}] = A, S_h, S_w, 5+C.
  * Also (re)sizes the activation arena.  Replaces nothing 1:1; the reference gets shapes from the tensors
@@ -83,6 +88,11 @@ int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, fl
  * op in milliseconds (op_ms[n_ops]); synchronises the stream.  Used by bench.py for the per-kernel roofline. */
 int yl_forward_profile(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
                        void* stream, float* op_ms /* host, n_ops */, int32_t n_ops);
+
+/* Run ONE op of a layer program on caller-provided NHWC device tensors (unit tests / micro-benchmarks of a
+ * single kernel).  blob_dev is the DEVICE copy of the weight blob the op's offsets refer to.                */
+int yl_run_op(const yl_op* op, const float* blob_dev, const float* in, const float* res, const float* up, float* out,
+              int32_t B, int32_t Hin, int32_t Win, int32_t Hu, int32_t Wu, int32_t use_tensor_cores, void* stream);
 
 /* Debug/parity tap: copy activation buffer `buf` ([B,H,W,C] NHWC fp32) of the last yl_forward into `dst`
  * (device).  dims receives H, W, C.  dst may be NULL to query dims only.                                */
@@ -121,6 +131,10 @@ int yl_decode(const float* const* level_logits, const int32_t* level_dims, int32
  * (x-mean)/std -> CHW.  nh,nw,left,top as computed by the host (int(round()) sizing).                  */
 int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t pitch, float* dst, int32_t S,
                   int32_t nh, int32_t nw, int32_t left, int32_t top, void* stream);
+
+/* Process-wide launch counters: key "tc_launches" (tcgen05 conv kernel), "simt_launches" (fp32 SIMT conv kernels),
+ * "post_launches".  Unknown key -> -1.  Lets tests assert WHICH kernel a call used.                       */
+long long yl_stat(const char* key);
 
 const char* yl_last_error(void);
 int yl_abi_version(void);

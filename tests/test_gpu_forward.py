@@ -18,12 +18,12 @@ def _engine(ckpt, **kw):
 
 
 @pytest.mark.parametrize("name", FWD_CASES)
-@pytest.mark.parametrize("fuse", [True, False])
-def test_forward_matches_golden_and_oracle(name, fuse):
+@pytest.mark.parametrize("fuse,tc", [(True, True), (False, True), (True, False)])
+def test_forward_matches_golden_and_oracle(name, fuse, tc):
     ckpt, k = case_ckpt(name)
     g = golden(name + ".npz")
     x = model_ref.synth_input(k["B"], k["img"], seed=k["input_seed"])
-    eng = _engine(ckpt, fuse_dwpw=fuse)
+    eng = _engine(ckpt, fuse_dwpw=fuse, tensor_cores=tc)
     outs = eng(x.cuda())
     torch.cuda.synchronize()
     want = model_ref.forward_ref(ckpt["state_dict"], ckpt["meta"], x)

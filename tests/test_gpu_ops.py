@@ -1,0 +1,182 @@
+"""Single-kernel numerics through yl_run_op: every conv kernel (fp32 SIMT and tcgen05 3xTF32) against a plain
+PyTorch fp32 (CPU) convolution of the same op.  Tolerance 2e-4 abs on O(1) activations (fp32 accumulation-order
+noise is ~1e-6; a single-pass TF32 product would show ~1e-2 here)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-4
+
+
+def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, w2=None, use_tc=1, nchw_input=False):
+    """w: [Cout,Cin,k,k] torch fp32 (dense) or [C,1,k,k] (depthwise); returns NHWC output (or head layout)."""
+    from yololite_b200 import _lib as L, packer
+    lib = L.lib()
+    blob, off = [], [0]
+
+    def add(a):
+        a = np.ascontiguousarray(a, np.float32).reshape(-1)
+        o = off[0]
+        blob.append(a)
+        pad = (-a.size) % 64
+        if pad:
+            blob.append(np.zeros(pad, np.float32))
+        off[0] += a.size + pad
+        return o
+    cout = w.shape[0]
+    wn = w.double().numpy()
+    op = L.YlOp()
+    op.kind, op.k, op.stride, op.act, op.anchors = kind, k, stride, act, anchors
+    op.src, op.dst, op.res, op.up = 0, 1, (2 if res is not None else -1), (3 if up is not None else -1)
+    op.k2, op.w2_off, op.wt_off = 0, -1, -1
+    if kind == L.OP_DW:
+        op.cin = op.cout = cout
+        op.w_off = add(np.transpose(wn, (2, 3, 1, 0)).reshape(k * k, cout))
+    elif kind == L.OP_STEM:
+        op.cin, op.cout = 3, cout
+        wm = np.transpose(wn, (2, 3, 1, 0)).reshape(-1, cout)
+        op.w_off = add(wm)
+    else:
+        op.cin, op.cout = w.shape[1], cout
+        wm = packer._gemm_w(wn)
+        op.w_off = add(wm)
+        op.wt_off = add(packer.tc_image(wm, cout))
+        if kind == L.OP_DWPW:
+            op.k, op.k2 = 1, 3
+            op.w2_off = add(np.transpose(w2.double().numpy(), (2, 3, 1, 0)).reshape(9, -1))
+    op.b_off = add(packer._pad4(bias.double().numpy())) if bias is not None else -1
+    dblob = torch.from_numpy(np.concatenate(blob)).cuda()
+    xin = x_nhwc.cuda().contiguous()
+    B = xin.shape[0]
+    Hin, Win = (xin.shape[2], xin.shape[3]) if nchw_input else (xin.shape[1], xin.shape[2])
+    kk = 3 if kind == L.OP_DWPW else k
+    ho, wo = (Hin + 2 * (k // 2) - k) // stride + 1, (Win + 2 * (k // 2) - k) // stride + 1
+    if kind == L.OP_DWPW:
+        ho, wo = Hin, Win
+    out = torch.full((B, ho, wo, cout), float("nan"), device="cuda")
+    rs = res.cuda().contiguous() if res is not None else None
+    us = up.cuda().contiguous() if up is not None else None
+    L.check(lib.yl_run_op(ctypes.byref(op), dblob.data_ptr(), xin.data_ptr(), rs.data_ptr() if rs is not None else None,
+                          us.data_ptr() if us is not None else None, out.data_ptr(), B, Hin, Win,
+                          us.shape[1] if us is not None else 0, us.shape[2] if us is not None else 0, use_tc, None))
+    torch.cuda.synchronize()
+    return out.cpu()
+
+
+def _ref(x_nchw, w, bias, k, stride, act, groups=1, res=None, up=None):
+    y = F.conv2d(x_nchw, w, bias, stride=stride, padding=k // 2, groups=groups)
+    if res is not None:
+        y = y + res.permute(0, 3, 1, 2)
+    if up is not None:
+        y = y + F.interpolate(up.permute(0, 3, 1, 2), size=y.shape[-2:], mode="nearest")
+    y = F.relu(y) if act == 1 else F.silu(y) if act == 2 else y
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("cin,cout,hw,act", [(16, 16, 40, 1), (48, 32, 20, 1), (32, 96, 24, 1), (96, 48, 17, 0), (64, 256, 10, 1),
+                                              (256, 64, 10, 0), (288, 64, 9, 0), (64, 480, 7, 1), (96, 96, 33, 2), (480, 96, 6, 0),
+                                              (244, 244, 5, 1)])
+def test_pointwise(use_tc, cin, cout, hw, act):
+    g = torch.Generator().manual_seed(cin * 1000 + cout)
+    x = torch.randn(3, hw, hw + 1, cin, generator=g)
+    w = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    got = _run(1, x, w, b, 1, 1, act, use_tc=use_tc)
+    want = _ref(x.permute(0, 3, 1, 2), w, b, 1, 1, act)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+def test_pointwise_residual_upsample_and_head_layout(use_tc):
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 13, 11, 48, generator=g)
+    w = torch.randn(96, 48, 1, 1, generator=g) / 7
+    b = torch.randn(96, generator=g)
+    res = torch.randn(2, 13, 11, 96, generator=g)
+    up = torch.randn(2, 7, 6, 96, generator=g)                       # 7x6 -> 13x11 is not an exact 2x
+    got = _run(1, x, w, b, 1, 1, 0, res=res, up=up, use_tc=use_tc)
+    want = _ref(x.permute(0, 3, 1, 2), w, b, 1, 1, 0, res=res, up=up)
+    assert float((got - want).abs().max()) <= TOL
+    # head layout: N = A*(5+C) stored as [B,A,H,W,5+C]
+    A, D = 2, 9
+    w = torch.randn(A * D, 48, 1, 1, generator=g) / 7
+    b = torch.randn(A * D, generator=g)
+    got = _run(1, x, w, b, 1, 1, 0, anchors=A, use_tc=use_tc).reshape(-1)
+    want = _ref(x.permute(0, 3, 1, 2), w, b, 1, 1, 0)               # [B,H,W,A*D]
+    want = want.view(2, 13, 11, A, D).permute(0, 3, 1, 2, 4).contiguous().reshape(-1)
+    assert float((got - want).abs().max()) <= TOL
+    # N = 85 (5+80 classes), A = 1: rows are not 16-byte aligned
+    w = torch.randn(85, 48, 1, 1, generator=g) / 7
+    b = torch.randn(85, generator=g)
+    got = _run(1, x, w, b, 1, 1, 0, anchors=1, use_tc=use_tc)
+    assert float((got - _ref(x.permute(0, 3, 1, 2), w, b, 1, 1, 0)).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("cin,cout,stride,hw,act", [(32, 16, 2, 40, 1), (16, 48, 2, 21, 1), (96, 96, 1, 12, 2), (96, 96, 2, 11, 1)])
+def test_dense3x3(use_tc, cin, cout, stride, hw, act):
+    g = torch.Generator().manual_seed(cin + cout + stride)
+    x = torch.randn(2, hw, hw + 2, cin, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    got = _run(1, x, w, b, 3, stride, act, use_tc=use_tc)
+    want = _ref(x.permute(0, 3, 1, 2), w, b, 3, stride, act)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+def test_stem_nchw(use_tc):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 3, 45, 52, generator=g)
+    w = torch.randn(32, 3, 3, 3, generator=g) / 5
+    b = torch.randn(32, generator=g)
+    got = _run(0, x, w, b, 3, 2, 1, use_tc=use_tc, nchw_input=True)
+    want = _ref(x, w, b, 3, 2, 1)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("k,stride", [(3, 1), (3, 2), (5, 1), (5, 2)])
+def test_depthwise(k, stride):
+    g = torch.Generator().manual_seed(k * 10 + stride)
+    x = torch.randn(2, 19, 23, 96, generator=g)
+    w = torch.randn(96, 1, k, k, generator=g) / k
+    b = torch.randn(96, generator=g)
+    got = _run(2, x, w, b, k, stride, 1)
+    want = _ref(x.permute(0, 3, 1, 2), w, b, k, stride, 1, groups=96)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("c,hw", [(96, 20), (96, 37), (244, 9)])
+def test_fused_dw_pw(use_tc, c, hw):
+    g = torch.Generator().manual_seed(c + hw)
+    x = torch.randn(2, hw, hw - 1, c, generator=g)
+    wd = torch.randn(c, 1, 3, 3, generator=g) / 3
+    wp = torch.randn(c, c, 1, 1, generator=g) / c ** 0.5
+    b = torch.randn(c, generator=g)
+    got = _run(3, x, wp, b, 1, 1, 1, w2=wd, use_tc=use_tc)
+    mid = F.conv2d(x.permute(0, 3, 1, 2), wd, None, padding=1, groups=c)
+    want = _ref(mid, wp, b, 1, 1, 1)
+    assert float((got - want).abs().max()) <= TOL
+
+
+def test_tensor_core_path_is_not_single_pass_tf32():
+    """The 3-pass split must recover fp32 accuracy: compare against an fp64 reference on a long-K product."""
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(1, 16, 16, 288, generator=g) * 4
+    w = torch.randn(64, 288, 1, 1, generator=g)
+    from yololite_b200 import _lib as L
+    n0 = L.lib().yl_stat(b"tc_launches")
+    got = _run(1, x, w, None, 1, 1, 0, use_tc=2).double()
+    assert L.lib().yl_stat(b"tc_launches") == n0 + 1          # the tcgen05 kernel really ran
+    want = F.conv2d(x.permute(0, 3, 1, 2).double(), w.double()).permute(0, 2, 3, 1)
+    rel = float((got - want).abs().max() / want.abs().max())
+    assert rel < 1e-5, rel          # measured 3e-6; single-pass TF32 gives ~5e-4 here
+    n1 = L.lib().yl_stat(b"simt_launches")
+    _run(1, x, w, None, 1, 1, 0, use_tc=0)
+    assert L.lib().yl_stat(b"simt_launches") == n1 + 1

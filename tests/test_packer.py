@@ -84,3 +84,24 @@ def test_product_synth_checkpoint_matches_reference_state_dict_spec():
     want = model_ref.forward_ref(ck["state_dict"], ck["meta"], x)
     for a, b in zip(outs, want):
         assert torch.isfinite(a).all() and float((a - b).abs().max()) < 2e-4
+
+
+def test_tc_weight_image_layout():
+    """[2][nslab][Npad][32] with hi/lo split and the SWIZZLE_128B chunk permutation, checked element by element."""
+    rng = np.random.RandomState(0)
+    for K, N in ((27, 32), (48, 85), (96, 96), (288, 16)):
+        wm = rng.randn(K, (N + 3) // 4 * 4)
+        img = packer.tc_image(wm, N)
+        nslab, npad = (K + 31) // 32, (N + 15) // 16 * 16
+        assert img.size == 2 * nslab * npad * 32
+        w32 = wm.astype(np.float32)
+        for _ in range(300):
+            k, n = int(rng.randint(0, nslab * 32)), int(rng.randint(0, npad))
+            s, kk = divmod(k, 32)
+            pos = (((kk // 4) ^ (n % 8)) * 4) + kk % 4
+            want = w32[k, n] if (k < K and n < N) else np.float32(0)
+            hi = packer.tf32_rn(np.array([want], np.float32))[0]
+            lo = packer.tf32_rn(np.array([want - hi], np.float32))[0]
+            assert img[((0 * nslab + s) * npad + n) * 32 + pos] == hi
+            assert img[((1 * nslab + s) * npad + n) * 32 + pos] == lo
+            assert abs(float(want) - float(hi) - float(lo)) <= abs(float(want)) * 2.0 ** -21

@@ -12,7 +12,7 @@ class YlOp(ctypes.Structure):
                 ("up", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("act", ctypes.c_int32), ("anchors", ctypes.c_int32),
                 ("k2", ctypes.c_int32), ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
-                ("w2_off", ctypes.c_int64), ("reserved", ctypes.c_int64)]
+                ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64)]
 
 
 OP_STEM, OP_CONV, OP_DW, OP_DWPW = 0, 1, 2, 3
@@ -26,6 +26,9 @@ _SIGNATURES = {
     "yl_engine_create": (ctypes.c_int, [ctypes.POINTER(YlOp), ctypes.c_int32, _P, ctypes.c_size_t, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P)]),
     "yl_engine_destroy": (ctypes.c_int, [_P]),
+    "yl_engine_set_option": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_int32]),
+    "yl_run_op": (ctypes.c_int, [ctypes.POINTER(YlOp), _P, _P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                 ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
     "yl_engine_plan": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "yl_forward": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P]),
     "yl_forward_profile": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P,
@@ -39,6 +42,7 @@ _SIGNATURES = {
                                  ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "yl_preprocess": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
+    "yl_stat": (ctypes.c_longlong, [ctypes.c_char_p]),
     "yl_last_error": (ctypes.c_char_p, []),
     "yl_abi_version": (ctypes.c_int, []),
     "yl_device_count": (ctypes.c_int, []),

@@ -10,6 +10,7 @@
 namespace yl {
 
 void set_error(const std::string& msg);
+extern long long g_tc_launches, g_simt_launches, g_post_launches;
 
 #define YL_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \

@@ -9,6 +9,7 @@
 namespace yl {
 
 static thread_local std::string g_err;
+long long g_tc_launches = 0, g_simt_launches = 0, g_post_launches = 0;
 void set_error(const std::string& msg) { g_err = msg; }
 
 struct BufShape {
@@ -31,9 +32,50 @@ struct yl_engine {
   std::vector<int> op_hout, op_wout, op_hin, op_win, op_hu, op_wu;
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
+  int use_tc = 1;
+  int sm_count = 148;
 };
 
 namespace yl {
+
+int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
+bool tc_plan(int K, int N, int* Nc, int* nchunks, int* stages);
+
+static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
+                  int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st) {
+  ConvParams p{};
+  p.in = in;
+  p.w = blob + op.w_off;
+  p.bias = op.b_off >= 0 ? blob + op.b_off : nullptr;
+  p.res = res; p.up = up;
+  p.w2 = op.w2_off >= 0 ? blob + op.w2_off : nullptr;
+  p.out = out;
+  p.B = B; p.Hin = hin; p.Win = win; p.Cin = op.cin;
+  p.Hout = hout; p.Wout = wout; p.Cout = op.cout;
+  p.KS = op.k; p.stride = op.stride; p.pad = op.k / 2;
+  p.Hu = hu; p.Wu = wu;
+  p.act = op.act; p.anchors = op.anchors;
+  if (op.kind == YL_OP_DWPW) { p.KS = op.k2; p.pad = op.k2 / 2; }     // geometry of the depthwise stage
+  if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {
+    const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
+    const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
+    int nc, nch, stg;
+    // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
+    // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
+    const bool big = (K >= 32 && op.cout >= 32) || use_tc == 2;
+    if (big && tc_plan(K, op.cout, &nc, &nch, &stg) && (op.cin & 3) == 0)
+    { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
+  }
+  ++g_simt_launches;
+  switch (op.kind) {
+    case YL_OP_STEM: return launch_stem(p, st);
+    case YL_OP_CONV: return launch_conv_gemm(p, st);
+    case YL_OP_DW: return launch_dw(p, st);
+    case YL_OP_DWPW: return launch_dwpw(p, st);
+    default: YL_REQUIRE(false, "unknown op kind");
+  }
+  return 0;
+}
 
 static int plan(yl_engine* e, int B, int H, int W) {
   if (e->B == B && e->H == H && e->W == W && e->arena) return 0;
@@ -94,6 +136,13 @@ static int plan(yl_engine* e, int B, int H, int W) {
 extern "C" {
 
 const char* yl_last_error(void) { return yl::g_err.c_str(); }
+long long yl_stat(const char* key) {
+  if (!key) return -1;
+  if (!std::strcmp(key, "tc_launches")) return yl::g_tc_launches;
+  if (!std::strcmp(key, "simt_launches")) return yl::g_simt_launches;
+  if (!std::strcmp(key, "post_launches")) return yl::g_post_launches;
+  return -1;
+}
 int yl_abi_version(void) { return YL_ABI_VERSION; }
 int yl_device_count(void) {
   int n = 0;
@@ -125,6 +174,7 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
   e->device = device;
   e->ops.assign(ops, ops + n_ops);
   e->n_buffers = n_buffers; e->n_levels = n_levels; e->blob_floats = blob_floats;
+  e->sm_count = prop.multiProcessorCount;
   if (cudaMalloc(&e->d_blob, blob_floats * sizeof(float)) != cudaSuccess ||
       cudaMemcpy(e->d_blob, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error(std::string("weight upload failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -143,6 +193,29 @@ int yl_engine_destroy(yl_engine* e) {
   if (e->d_blob) cudaFree(e->d_blob);
   delete e;
   return 0;
+}
+
+int yl_engine_set_option(yl_engine* e, const char* key, int32_t value) {
+  using namespace yl;
+  YL_REQUIRE(e && key, "null argument");
+  if (std::strcmp(key, "tensor_cores") == 0) { e->use_tc = value ? 1 : 0; return 0; }
+  YL_REQUIRE(false, "unknown engine option");
+  return -1;
+}
+
+int yl_run_op(const yl_op* op, const float* blob_dev, const float* in, const float* res, const float* up, float* out,
+              int32_t B, int32_t Hin, int32_t Win, int32_t Hu, int32_t Wu, int32_t use_tensor_cores, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(op && blob_dev && in && out, "null argument");
+  YL_REQUIRE(op->k >= 1 && (op->k & 1) && op->stride >= 1, "bad conv geometry");
+  int dev = 0;
+  YL_CHECK_CUDA(cudaGetDevice(&dev));
+  int sms = 0;
+  YL_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int pad = op->k / 2;
+  const int hout = (Hin + 2 * pad - op->k) / op->stride + 1, wout = (Win + 2 * pad - op->k) / op->stride + 1;
+  return run_op(*op, blob_dev, in, res, up, out, B, Hin, Win, hout, wout, Hu, Wu, use_tensor_cores, sms,
+                reinterpret_cast<cudaStream_t>(stream));
 }
 
 int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shapes) {
@@ -165,31 +238,16 @@ static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int3
   auto bufptr = [&](int id) -> float* { return reinterpret_cast<float*>(e->arena + e->bufs[id].off); };
   for (size_t i = 0; i < e->ops.size(); ++i) {
     const yl_op& op = e->ops[i];
-    ConvParams p{};
-    p.in = op.src == YL_SRC_INPUT ? x : bufptr(op.src);
-    p.w = e->d_blob + op.w_off;
-    p.bias = op.b_off >= 0 ? e->d_blob + op.b_off : nullptr;
-    p.res = op.res >= 0 ? bufptr(op.res) : nullptr;
-    p.up = op.up >= 0 ? bufptr(op.up) : nullptr;
-    p.w2 = op.w2_off >= 0 ? e->d_blob + op.w2_off : nullptr;
-    if (op.dst >= 0) p.out = bufptr(op.dst);
+    const float* in = op.src == YL_SRC_INPUT ? x : bufptr(op.src);
+    float* outp;
+    if (op.dst >= 0) outp = bufptr(op.dst);
     else {
-      p.out = level_out[-op.dst - 1];
-      YL_REQUIRE(p.out, "null level output pointer");
+      outp = level_out[-op.dst - 1];
+      YL_REQUIRE(outp, "null level output pointer");
     }
-    p.B = B; p.Hin = e->op_hin[i]; p.Win = e->op_win[i]; p.Cin = op.cin;
-    p.Hout = e->op_hout[i]; p.Wout = e->op_wout[i]; p.Cout = op.cout;
-    p.KS = op.k; p.stride = op.stride; p.pad = op.k / 2;
-    p.Hu = e->op_hu[i]; p.Wu = e->op_wu[i];
-    p.act = op.act; p.anchors = op.anchors;
-    int rc = 0;
-    switch (op.kind) {
-      case YL_OP_STEM: rc = launch_stem(p, st); break;
-      case YL_OP_CONV: rc = launch_conv_gemm(p, st); break;
-      case YL_OP_DW: rc = launch_dw(p, st); break;
-      case YL_OP_DWPW: p.KS = op.k2; p.pad = op.k2 / 2; rc = launch_dwpw(p, st); break;
-      default: YL_REQUIRE(false, "unknown op kind");
-    }
+    int rc = run_op(op, e->d_blob, in, op.res >= 0 ? bufptr(op.res) : nullptr, op.up >= 0 ? bufptr(op.up) : nullptr, outp, B,
+                    e->op_hin[i], e->op_win[i], e->op_hout[i], e->op_wout[i], e->op_hu[i], e->op_wu[i], e->use_tc,
+                    e->sm_count, st);
     if (rc) return rc;
     if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
   }

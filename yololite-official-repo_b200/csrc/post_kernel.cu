@@ -446,6 +446,7 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
     smem_set = smem;
   }
   const unsigned grid = (unsigned)B * (unsigned)p.tile_off[n_levels];
+  ++g_post_launches;
   post_kernel<<<grid, POST_THREADS, smem, st>>>(p);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;

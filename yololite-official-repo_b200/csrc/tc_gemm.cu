@@ -1,0 +1,464 @@
+// tcgen05 implicit-GEMM convolution with error-compensated 3xTF32 operands (sm_100a).
+//
+//   C[M, N] = A[M, K] * W[K, N]      M = B*Hout*Wout pixels, K = taps*Cin, N = Cout
+//
+// Why 3xTF32: the parity bar is 1e-3 abs on logits after a 69-conv stack; single-pass TF32/BF16/FP16 operands
+// miss it by two orders of magnitude, fp32 SIMT FMA is ~5x below the HBM roofline
+// for the 96-channel pointwise layers.  Every fp32 operand x is split exactly into hi = x & 0xFFFFE000 (a TF32
+// value) and lo = x - hi; D = Ahi*Whi + Alo*Whi + Ahi*Wlo accumulates in fp32 in TMEM (dropped term ~2^-22).
+//
+// Structure (one persistent CTA per SM, 13 warps, warp-specialised):
+//   warps 0-7  producers: read the A tile from HBM with coalesced 16 B loads (or compute it: depthwise 3x3 for the
+//              fused DWConvBlock, im2col gather for dense 3x3, NCHW gather for the stem), split hi/lo in registers,
+//              st.shared into the canonical K-major SWIZZLE_128B UMMA layout (32 fp32 = one 128 B row per K-slab),
+//              fence.proxy.async, arrive on the stage's "full" mbarrier;
+//   warp  12   one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Nc, K=8 per instruction,
+//              3 passes per k-step) into one of two TMEM accumulators, tcgen05.commit frees the smem stage /
+//              publishes the accumulator;
+//   warps 8-11 epilogue: tcgen05.ld 32 lanes x 16 columns, + bias (folded BN) + residual + nearest-upsampled
+//              coarser level + ReLU/SiLU, 16 B stores (head layout [B,A,S,S,5+C] written directly).
+// The weight image (hi and lo, pre-split and pre-swizzled on the host) stays resident in shared memory for the
+// CTA's lifetime.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
+#include "common.cuh"
+
+namespace yl {
+
+constexpr int TC_PROD_WARPS = 8;                 // producer warps
+constexpr int TC_EPI_WARP0 = 8;                  // epilogue warps 8..11 (warp % 4 == TMEM lane quarter)
+constexpr int TC_MMA_WARP = 12;
+constexpr int TC_THREADS = 32 * 13;
+constexpr int TC_BM = 128;
+constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one K-slab (32 fp32) of the A tile
+constexpr int TC_SMEM_BUDGET = 224 * 1024;
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_AUX_BYTES = 256 + 4 * 32 * 33 * 4;   // barriers + tmem slot + epilogue transpose staging
+
+struct TcParams {
+  ConvParams c;
+  const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
+  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise3x3->pointwise
+  int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
+  long long M;
+  int num_tiles;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) asm volatile("trap;");   // protocol error: fail loudly, never hang the device
+  }
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor: start[0,14) LBO[16,30) SBO[32,46)
+  // version[46,48)=1 layout[61,64)=2)
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// round-to-nearest onto the TF32 grid (10 explicit mantissa bits): unbiased, and exact for the tensor core
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned char* lo_base, int row, int chunk, float4 a) {
+  const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
+  float4 h, l;
+  h.x = tf32_rn(a.x); h.y = tf32_rn(a.y); h.z = tf32_rn(a.z); h.w = tf32_rn(a.w);
+  l.x = tf32_rn(a.x - h.x); l.y = tf32_rn(a.y - h.y); l.z = tf32_rn(a.z - h.z); l.w = tf32_rn(a.w - h.w);
+  *reinterpret_cast<float4*>(hi_base + off) = h;
+  *reinterpret_cast<float4*>(lo_base + off) = l;
+}
+
+// SiLU / ReLU through one out-of-line helper keeps the (I-cache sensitive) epilogue small.
+__device__ __noinline__ float4 act4(float4 o, int act) {
+  if (act == YL_ACT_RELU) {
+    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+  } else if (act == YL_ACT_SILU) {
+    o.x = silu_accurate(o.x); o.y = silu_accurate(o.y); o.z = silu_accurate(o.z); o.w = silu_accurate(o.w);
+  }
+  return o;
+}
+
+// One 16 B element of the A tile for output row (b, oy, ox) [already offset by stride/pad in (iy0, ix0)] at k.
+template <int MODE>
+__device__ __forceinline__ float4 load_a(const ConvParams& c, const float* rbase, int iy0, int ix0, int k, int tap_y, int tap_x,
+                                         int ci) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (MODE == 0) {
+    a = __ldg(reinterpret_cast<const float4*>(rbase + k));
+  } else if (MODE == 1) {
+    const int iy = iy0 + tap_y, ix = ix0 + tap_x;
+    if (iy >= 0 && iy < c.Hin && ix >= 0 && ix < c.Win)
+      a = __ldg(reinterpret_cast<const float4*>(rbase + ((size_t)iy * c.Win + ix) * c.Cin + ci));
+  } else {   // depthwise 3x3 (pad 1, stride 1) computed on the fly
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = iy0 + ky;
+      if (iy < 0 || iy >= c.Hin) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ix0 + kx;
+        if (ix < 0 || ix >= c.Win) continue;
+        const float4 x4 = __ldg(reinterpret_cast<const float4*>(rbase + ((size_t)iy * c.Win + ix) * c.Cin + k));
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(c.w2 + (ky * 3 + kx) * c.Cin + k));
+        a.x = fmaf(x4.x, w4.x, a.x); a.y = fmaf(x4.y, w4.y, a.y);
+        a.z = fmaf(x4.z, w4.z, a.z); a.w = fmaf(x4.w, w4.w, a.w);
+      }
+    }
+  }
+  return a;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const ConvParams& c = p.c;
+  const int M = (int)p.M;
+
+  // ---- shared memory carve-up (all slabs 1024 B aligned)
+  const uint32_t w_slab_bytes = (uint32_t)p.Nc * 128u;
+  unsigned char* w_hi = smem;
+  unsigned char* w_lo = w_hi + (size_t)p.nslab * w_slab_bytes;
+  unsigned char* a_ring = w_lo + (size_t)p.nslab * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES);
+  uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
+  uint64_t* empty_bar = bars + TC_MAX_STAGES;      // [stages]   MMA commit -> producers (count 1)
+  uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA         (count 4)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 x 33 floats (padded transpose)
+
+  const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), TC_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TC_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // resident weight image: hi then lo, every slab's rows [chunk_n0, chunk_n0+Nc)
+  {
+    const int per_slab4 = p.Nc * 8;                                 // float4 per slab
+    const int total4 = 2 * p.nslab * per_slab4;
+    for (int i = threadIdx.x; i < total4; i += TC_THREADS) {
+      const int ps = i / per_slab4, r = i - ps * per_slab4;          // ps = pass*nslab + slab
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (chunk_n0 + (r >> 3) < p.Npad)
+        v = __ldg(reinterpret_cast<const float4*>(p.wimg) + ((size_t)ps * p.Npad + chunk_n0) * 8 + r);
+      reinterpret_cast<float4*>(w_hi)[(size_t)ps * per_slab4 + r] = v;
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles = p.num_tiles;
+
+  if (warp < TC_PROD_WARPS) {
+    // =============================== producers ===============================
+    // 256 threads; per K-slab each thread owns 4 x 16 B: rows (t>>3)+32*i, chunk t&7.  Two slabs are loaded back to
+    // back (8 independent 16 B loads in flight per thread, issued BEFORE waiting for the smem stage), then split + stored.
+    const int t = threadIdx.x;                      // 0..255
+    const int ch = t & 7, r0 = t >> 3;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = tile * TC_BM;
+      const float* rbase[4];
+      int roy[4], rox[4];
+      bool rok[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + r0 + 32 * i;
+        rok[i] = m < M;
+        const int mm = rok[i] ? m : 0;
+        if (MODE == 0) {
+          rbase[i] = c.in + (size_t)mm * c.Cin;
+          roy[i] = rox[i] = 0;
+        } else {
+          const int hw = c.Wout * c.Hout;
+          const int b = mm / hw, rem = mm - b * hw;
+          const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+          rbase[i] = c.in + (size_t)b * c.Hin * c.Win * c.Cin;
+          roy[i] = oy * c.stride - c.pad;
+          rox[i] = ox * c.stride - c.pad;
+        }
+      }
+      for (int s = 0; s < p.nslab; s += 2) {
+        const int ns = min(2, p.nslab - s);
+        float4 v[2][4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int k = (s + u) * 32 + ch * 4;
+          int tap_y = 0, tap_x = 0, ci = k;
+          if (MODE == 1) {
+            const int tap = k / c.Cin;
+            ci = k - tap * c.Cin;
+            tap_y = tap / c.KS;
+            tap_x = tap - tap_y * c.KS;
+          }
+          const bool kok = u < ns && k < p.K;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[u][i] = (kok && rok[i]) ? load_a<MODE>(c, rbase[i], roy[i], rox[i], k, tap_y, tap_x, ci)
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u < ns) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+            unsigned char* lo = hi + TC_SLAB_BYTES;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split_store(hi, lo, r0 + 32 * i, ch, v[u][i]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == TC_MMA_WARP) {
+    // =============================== MMA issuer ===============================
+    // Two accumulators per tile: `main` takes Ahi*Whi, `corr` takes Alo*Whi + Ahi*Wlo.  The tensor core truncates its fp32
+    // accumulator on every instruction, which biases a long accumulation chain; keeping the (2^-11 smaller) correction
+    // terms in their own accumulator cuts the chain on the big one to K/8 steps.  The epilogue adds the two in fp32.
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * p.Nc);
+        const uint32_t d_corr = d_main + (uint32_t)p.Nc;
+        uint32_t first = 0;
+        for (int s = 0; s < p.nslab; ++s) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_u32(a_ring + (size_t)stage * 2 * TC_SLAB_BYTES);
+          const uint32_t a_lo = a_hi + TC_SLAB_BYTES;
+          const uint32_t b_hi = smem_u32(w_hi + (size_t)s * w_slab_bytes);
+          const uint32_t b_lo = smem_u32(w_lo + (size_t)s * w_slab_bytes);
+          const int ksteps = min(4, (p.K - s * 32 + 7) >> 3);
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t ko = (uint32_t)j * 32u;          // 8 fp32 = 32 B along K inside the 128 B swizzle row
+            mma_tf32(d_corr, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
+            mma_tf32(d_corr, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
+            mma_tf32(d_main, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+            first = 1;
+          }
+          mma_commit(smem_u32(&empty_bar[stage]));           // frees this A stage once the MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        mma_commit(smem_u32(&tfull_bar[acc]));               // accumulators complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    // TMEM -> registers (lane = row) -> padded smem transpose -> coalesced 16 B global accesses (lane = 4 columns,
+    // 8 lanes per 128 B row segment): bias, residual and the upsampled coarser level are read with the same mapping.
+    const int q = warp - TC_EPI_WARP0;                        // TMEM lane quarter == warp index % 4
+    const int N = c.Cout;
+    const int D = c.anchors > 0 ? N / c.anchors : N;
+    float* stg = epi_stage + q * (32 * 33);
+    const bool vec = (N & 3) == 0 && c.anchors <= 1;
+    const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
+    const int hw = c.Wout * c.Hout;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int mw = tile * TC_BM + q * 32;                   // first row of this warp
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.Nc);
+      for (int col = 0; col < p.Nc; col += 32) {
+        const int wcols = min(32, p.Nc - col);                // 32, or 16 for the last block
+        {
+          float v[16], w[16];
+          tmem_ld16(taddr + (uint32_t)col, v);
+          tmem_ld16(taddr + (uint32_t)(p.Nc + col), w);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) stg[lane * 33 + j] = v[j] + w[j];
+          if (wcols > 16) {
+            tmem_ld16(taddr + (uint32_t)col + 16, v);
+            tmem_ld16(taddr + (uint32_t)(p.Nc + col) + 16, w);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) stg[lane * 33 + 16 + j] = v[j] + w[j];
+          }
+        }
+        __syncwarp();
+        const int nb = chunk_n0 + col;                        // first global column of the block
+        if (vec) {
+          const int n = nb + vc;
+          if (vc < wcols && n < N) {
+            const float4 bia = c.bias ? __ldg(reinterpret_cast<const float4*>(c.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+            for (int it = 0; it < 8; ++it) {
+              const int r = vr + 4 * it;
+              const int m = mw + r;
+              if (m < M) {
+                const float* sp = stg + r * 33 + vc;
+                float4 o = make_float4(sp[0] + bia.x, sp[1] + bia.y, sp[2] + bia.z, sp[3] + bia.w);
+                if (c.res) {
+                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(c.res + (size_t)m * N + n));
+                  o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
+                }
+                if (c.up) {
+                  const int b = m / hw, rem = m - b * hw;
+                  const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+                  const size_t uo = (((size_t)b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N;
+                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(c.up + uo + n));
+                  o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
+                }
+                if (c.act) o = act4(o, c.act);
+                *reinterpret_cast<float4*>(c.out + (size_t)m * N + n) = o;
+              }
+            }
+          }
+        } else {
+          const int n = nb + lane;                            // scalar path: lane = column, one row per instruction
+          if (lane < wcols && n < N) {
+            const float bia = c.bias ? __ldg(c.bias + n) : 0.f;
+            const int a = n / D, dd = n - a * D;
+            for (int r = 0; r < 32; ++r) {
+              const int m = mw + r;
+              if (m >= M) break;
+              float o = stg[r * 33 + lane] + bia;
+              if (c.res) o += __ldg(c.res + (size_t)m * N + n);
+              size_t oidx = (size_t)m * N + n;
+              if (c.up || c.anchors > 1) {
+                const int b = m / hw, rem = m - b * hw;
+                const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+                if (c.up)
+                  o += __ldg(c.up + (((size_t)b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N + n);
+                if (c.anchors > 1) oidx = ((((size_t)b * c.anchors + a) * c.Hout + oy) * c.Wout + ox) * D + dd;
+              }
+              c.out[oidx] = act_fn(o, c.act);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == TC_MMA_WARP) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+// Decide whether (K, N) fits the resident-weight design and how N is chunked.  Shared with the packer through
+// the image layout only ([2][nslab][Npad][32]), which does not depend on the chunking.
+bool tc_plan(int K, int N, int* Nc_out, int* nchunks_out, int* stages_out) {
+  if (K < 8 || N < 8) return false;
+  const int nslab = (K + 31) / 32;
+  const int Npad = (N + 15) / 16 * 16;
+  for (int nch = 1; nch <= 4; ++nch) {
+    int Nc = ((Npad / 16 + nch - 1) / nch) * 16;
+    if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
+    const size_t wbytes = (size_t)2 * nslab * Nc * 128;
+    const size_t fixed = wbytes + TC_AUX_BYTES + 1024;
+    if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
+    int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    *Nc_out = Nc; *nchunks_out = nch; *stages_out = stages;
+    return true;
+  }
+  return false;
+}
+
+int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st) {
+  TcParams p{};
+  p.c = c;
+  p.wimg = wimg;
+  p.mode = mode;
+  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
+  p.nslab = (p.K + 31) / 32;
+  p.Npad = (c.Cout + 15) / 16 * 16;
+  YL_REQUIRE(tc_plan(p.K, c.Cout, &p.Nc, &p.nchunks, &p.stages), "shape does not fit the tcgen05 conv kernel");
+  YL_REQUIRE(mode != 3 && (c.Cin & 3) == 0, "tcgen05 conv needs NHWC input with Cin % 4 == 0");
+  p.M = (long long)c.B * c.Hout * c.Wout;
+  p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  YL_REQUIRE(p.M < (1ll << 31) - TC_BM, "too many output pixels for 32-bit row indices");
+  int cols = 32;
+  while (cols < 4 * p.Nc) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES + 1024;
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
+    attr_set = true;
+  }
+  int gx = sm_count / p.nchunks;
+  if (gx < 1) gx = 1;
+  if (gx > p.num_tiles) gx = p.num_tiles;
+  dim3 grid(gx, p.nchunks);
+  if (mode == 0) tc_conv_kernel<0><<<grid, TC_THREADS, smem, st>>>(p);
+  else if (mode == 1) tc_conv_kernel<1><<<grid, TC_THREADS, smem, st>>>(p);
+  else tc_conv_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
+  YL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace yl

@@ -22,7 +22,7 @@ def _stream_ptr(device) -> ctypes.c_void_p:
 
 class YoloLiteB200:
     def __init__(self, state_dict: dict, meta: dict, device="cuda:0", fuse_dwpw: bool = True,
-                 reuse_buffers: bool = True):
+                 reuse_buffers: bool = True, tensor_cores: bool = True):
         lib = L.lib()                                   # raises ImportError if the extension is not built
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -30,7 +30,8 @@ class YoloLiteB200:
         if not torch.cuda.is_available():
             raise RuntimeError("no CUDA device visible: yololite_b200 has no CPU fallback")
         self.meta = meta
-        self.program = packer.lower(state_dict, meta, fuse_dwpw=fuse_dwpw, reuse_buffers=reuse_buffers)
+        self.program = packer.lower(state_dict, meta, fuse_dwpw=fuse_dwpw, reuse_buffers=reuse_buffers,
+                                    tensor_cores=tensor_cores)
         cfg = self.program.cfg
         self.cfg = cfg
         self.num_classes = cfg.num_classes
@@ -49,6 +50,7 @@ class YoloLiteB200:
                                      self.program.n_buffers, self._n_levels, idx, ctypes.byref(h)))
         self._h = h
         self._dev_index = idx
+        L.check(lib.yl_engine_set_option(h, b"tensor_cores", 1 if tensor_cores else 0))
         self._shape_cache = {}
 
     # ---- reference-compatible surface

@@ -151,13 +151,41 @@ def _gemm_w(w: np.ndarray) -> np.ndarray:
     return out
 
 
+def tf32_rn(x: np.ndarray) -> np.ndarray:
+    """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits) -- same bit trick as the kernel's producers."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
+    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tc_image(wm: np.ndarray, n_out: int) -> np.ndarray:
+    """tcgen05 weight image of a GEMM matrix wm [K][>=n_out] (fp64, BN folded): [2 (hi,lo)][ceil(K/32)][ceil16(N)][32] fp32.
+
+    hi = tf32_rn(w), lo = tf32_rn(w - hi).  Each K-slab is the K-major SWIZZLE_128B canonical UMMA layout:
+    row n holds 32 consecutive k as 8 chunks of 16 B, chunk c stored at position c ^ (n % 8)."""
+    K = wm.shape[0]
+    nslab, npad = (K + 31) // 32, (n_out + 15) // 16 * 16
+    w = np.zeros((nslab * 32, npad), np.float32)
+    w[:K, :n_out] = wm[:, :n_out].astype(np.float32)
+    hi = tf32_rn(w)
+    lo = tf32_rn((w - hi).astype(np.float32))
+    out = np.empty((2, nslab, npad, 8, 4), np.float32)
+    n = np.arange(npad)
+    for pi, x in enumerate((hi, lo)):
+        t = x.reshape(nslab, 8, 4, npad).transpose(0, 3, 1, 2)          # [slab][n][chunk][4]
+        dst = out[pi]
+        for c in range(8):
+            dst[:, n, c ^ (n % 8), :] = t[:, n, c, :]
+    return out.reshape(-1)
+
+
 def _pad4(b: np.ndarray) -> np.ndarray:
     out = np.zeros(((b.size + 3) // 4 * 4,), np.float64)
     out[:b.size] = b
     return out
 
 
-def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True) -> Program:
+def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True,
+          tensor_cores: bool = True) -> Program:
     cfg = parse_meta(meta)
     sd = _SD(state_dict)
     P = Program(cfg=cfg)
@@ -169,7 +197,9 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
                           res=(-1 if res is None else res.vid), up=(-1 if up is None else up.vid),
                           cin=(3 if src is None else src.C), cout=cout, k=k, stride=stride, act=act, anchors=anchors, k2=k2,
                           w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
-                          w2_off=(-1 if w2 is None else P.add_blob(w2))))
+                          w2_off=(-1 if w2 is None else P.add_blob(w2)),
+                          wt_off=(P.add_blob(tc_image(np.asarray(w, np.float64).reshape(-1, w.shape[-1]), cout))
+                                  if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW) and cout >= 8 and w.shape[0] >= 8 else -1)))
         return dst
 
     def conv_bn(x: Optional[_T], wkey, bnkey, k, stride, act, red, res=None) -> _T:
@@ -329,9 +359,8 @@ def to_c(P: Program):
     for i, op in enumerate(P.ops):
         o = arr[i]
         for f in ("kind", "src", "dst", "res", "up", "cin", "cout", "k", "stride", "act", "anchors", "k2", "w_off", "b_off",
-                  "w2_off"):
+                  "w2_off", "wt_off"):
             setattr(o, f, int(op[f]))
-        o.reserved = 0
     blob = np.concatenate(P.blob).astype(np.float32, copy=False)
     assert blob.size == P.blob_len
     return arr, blob
