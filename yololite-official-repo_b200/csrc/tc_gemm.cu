@@ -19,6 +19,8 @@
 //              coarser level + ReLU/SiLU, 16 B stores (head layout [B,A,S,S,5+C] written directly).
 // The weight image (hi and lo, pre-split and pre-swizzled on the host) stays resident in shared memory for the
 // CTA's lifetime.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace yl {
@@ -31,13 +33,16 @@ constexpr int TC_BM = 128;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one K-slab (32 fp32) of the A tile
 constexpr int TC_SMEM_BUDGET = 224 * 1024;
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_AUX_BYTES = 256 + 4 * 32 * 33 * 4;   // barriers + tmem slot + epilogue transpose staging
+constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
+constexpr int TC_AUX_BYTES = 256 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
 
 struct TcParams {
   ConvParams c;
   const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
   int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise3x3->pointwise
   int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
+  int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
+  int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
   long long M;
   int num_tiles;
 };
@@ -96,6 +101,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // round-to-nearest onto the TF32 grid (10 explicit mantissa bits): unbiased, and exact for the tensor core
 __device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned char* lo_base, int row, int chunk, float4 a) {
   const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA         (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 x 33 floats (padded transpose)
+  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 rows x TC_EPI_PITCH floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
 
@@ -200,40 +217,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 
   if (warp < TC_PROD_WARPS) {
     // =============================== producers ===============================
-    // 256 threads; per K-slab each thread owns 4 x 16 B: rows (t>>3)+32*i, chunk t&7.  Two slabs are loaded back to
-    // back (8 independent 16 B loads in flight per thread, issued BEFORE waiting for the smem stage), then split + stored.
+    // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
     const int ch = t & 7, r0 = t >> 3;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int m0 = tile * TC_BM;
-      const float* rbase[4];
-      int roy[4], rox[4];
-      bool rok[4];
+    if (MODE != 2) {
+      // cp.async pipeline: the 16 B pieces are copied global -> shared (zero-filled outside the image / past K) straight
+      // into their swizzled slot of the stage's `hi` slab, up to `depth` K-slabs ahead of the one being converted, so
+      // tens of KB per SM are in flight without holding registers.  Each thread then rewrites ITS OWN pieces in place as
+      // hi = rn_tf32(a) and stores lo = rn_tf32(a - hi) -- no cross-thread dependency, no extra barrier.
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = my_tiles * p.nslab;
+      const int depth = min(p.stages - 1, 3);
+      uint32_t soff[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int m = m0 + r0 + 32 * i;
-        rok[i] = m < M;
-        const int mm = rok[i] ? m : 0;
-        if (MODE == 0) {
-          rbase[i] = c.in + (size_t)mm * c.Cin;
-          roy[i] = rox[i] = 0;
-        } else {
-          const int hw = c.Wout * c.Hout;
-          const int b = mm / hw, rem = mm - b * hw;
-          const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
-          rbase[i] = c.in + (size_t)b * c.Hin * c.Win * c.Cin;
-          roy[i] = oy * c.stride - c.pad;
-          rox[i] = ox * c.stride - c.pad;
-        }
+        const int row = r0 + 32 * i;
+        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
       }
-      for (int s = 0; s < p.nslab; s += 2) {
-        const int ns = min(2, p.nslab - s);
-        float4 v[2][4];
+      const uint32_t ring = smem_u32(a_ring);
+      int issued = 0, i_tile = blockIdx.x, i_s = 0, i_stage = 0;
+      uint32_t i_phase = 0;
+      const float* rbase[4] = {c.in, c.in, c.in, c.in};
+      int roy[4] = {0, 0, 0, 0}, rox[4] = {0, 0, 0, 0};
+      bool rok[4] = {false, false, false, false};
+      int c_stage = 0;
+      for (int j = 0; j < total; ++j) {
+        while (issued < total && issued <= j + depth) {
+          if (i_s == 0) {                            // new tile: per-row geometry
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int k = (s + u) * 32 + ch * 4;
+            for (int i = 0; i < 4; ++i) {
+              const int m = i_tile * TC_BM + r0 + 32 * i;
+              rok[i] = m < M;
+              const int mm = rok[i] ? m : 0;
+              if (MODE == 0) {
+                rbase[i] = c.in + (size_t)mm * c.Cin;
+              } else {
+                const int hw = c.Wout * c.Hout;
+                const int b = mm / hw, rem = mm - b * hw;
+                const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+                rbase[i] = c.in + (size_t)b * c.Hin * c.Win * c.Cin;
+                roy[i] = oy * c.stride - c.pad;
+                rox[i] = ox * c.stride - c.pad;
+              }
+            }
+          }
+          const int k = i_s * 32 + ch * 4;
           int tap_y = 0, tap_x = 0, ci = k;
           if (MODE == 1) {
             const int tap = k / c.Cin;
@@ -241,25 +269,94 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
             tap_y = tap / c.KS;
             tap_x = tap - tap_y * c.KS;
           }
-          const bool kok = u < ns && k < p.K;
+          mbar_wait(smem_u32(&empty_bar[i_stage]), i_phase ^ 1);
+          const uint32_t dst = ring + (uint32_t)i_stage * 2u * TC_SLAB_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float* src = c.in;
+            uint32_t nbytes = 0;
+            if (rok[i] && k < p.K) {
+              if (MODE == 0) {
+                src = rbase[i] + k; nbytes = 16;
+              } else {
+                const int iy = roy[i] + tap_y, ix = rox[i] + tap_x;
+                if (iy >= 0 && iy < c.Hin && ix >= 0 && ix < c.Win) {
+                  src = rbase[i] + ((size_t)iy * c.Win + ix) * c.Cin + ci; nbytes = 16;
+                }
+              }
+            }
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + soff[i]), "l"(src), "r"(nbytes) : "memory");
+          }
+          asm volatile("cp.async.commit_group;" ::: "memory");
+          ++issued;
+          if (++i_s == p.nslab) { i_s = 0; i_tile += gridDim.x; }
+          if (++i_stage == p.stages) { i_stage = 0; i_phase ^= 1; }
+        }
+        switch (issued - j - 1) {                    // groups allowed to stay in flight
+          case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+          case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+          case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+          default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        }
+        unsigned char* hi = a_ring + (size_t)c_stage * 2 * TC_SLAB_BYTES;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4* ph = reinterpret_cast<float4*>(hi + soff[i]);
+          const float4 a = *ph;
+          float4 h, l;
+          if (p.raw_hi) {      // hi = what the tensor core will read: the value with the low 13 mantissa bits dropped
+            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+          } else {
+            h.x = tf32_rn(a.x); h.y = tf32_rn(a.y); h.z = tf32_rn(a.z); h.w = tf32_rn(a.w);
+            l.x = tf32_rn(a.x - h.x); l.y = tf32_rn(a.y - h.y); l.z = tf32_rn(a.z - h.z); l.w = tf32_rn(a.w - h.w);
+            *ph = h;
+          }
+          *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[c_stage]));
+        if (++c_stage == p.stages) c_stage = 0;
+      }
+    } else {
+      // fused DWConvBlock: the depthwise 3x3 is computed in registers while loading (one K-slab per round)
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = tile * TC_BM;
+        const float* rbase[4];
+        int roy[4], rox[4];
+        bool rok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int m = m0 + r0 + 32 * i;
+          rok[i] = m < M;
+          const int mm = rok[i] ? m : 0;
+          const int hw = c.Wout * c.Hout;
+          const int b = mm / hw, rem = mm - b * hw;
+          const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+          rbase[i] = c.in + (size_t)b * c.Hin * c.Win * c.Cin;
+          roy[i] = oy * c.stride - c.pad;
+          rox[i] = ox * c.stride - c.pad;
+        }
+        for (int s = 0; s < p.nslab; ++s) {
+          const int k = s * 32 + ch * 4;
+          float4 v[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            v[u][i] = (kok && rok[i]) ? load_a<MODE>(c, rbase[i], roy[i], rox[i], k, tap_y, tap_x, ci)
-                                      : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            v[i] = (k < p.K && rok[i]) ? load_a<2>(c, rbase[i], roy[i], rox[i], k, 0, 0, k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+          unsigned char* lo = hi + TC_SLAB_BYTES;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          if (u < ns) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-            unsigned char* lo = hi + TC_SLAB_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) split_store(hi, lo, r0 + 32 * i, ch, v[u][i]);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
+          for (int i = 0; i < 4; ++i) split_store(hi, lo, r0 + 32 * i, ch, v[i]);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -310,70 +407,122 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
     const int q = warp - TC_EPI_WARP0;                        // TMEM lane quarter == warp index % 4
     const int N = c.Cout;
     const int D = c.anchors > 0 ? N / c.anchors : N;
-    float* stg = epi_stage + q * (32 * 33);
+    float* stg = epi_stage + q * (32 * TC_EPI_PITCH);
     const bool vec = (N & 3) == 0 && c.anchors <= 1;
+    // dense staging: N not a multiple of 4 (head outputs, 5+C channels), single chunk, plain [M][N] output
+    const bool dense = p.dense_epi != 0;
+    float* dstg = epi_stage + 4 * 32 * TC_EPI_PITCH + q * (32 * p.Nc);
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp
+      const int rows_ok = min(32, M - mw);                    // rows of this warp inside the matrix
+      // element offsets of the nearest-upsample source row for the 8 rows this lane owns (one division per tile)
+      int up_off[8];
+      if (c.up && (vec || dense)) {
+        int m = min(mw + vr, M - 1);
+        int b = m / hw, rem = m - b * hw;
+        int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          up_off[it] = ((b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N;
+          ox += 4;
+          while (ox >= c.Wout) { ox -= c.Wout; if (++oy == c.Hout) { oy = 0; if (b + 1 < c.B) ++b; } }
+        }
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.Nc);
       for (int col = 0; col < p.Nc; col += 32) {
         const int wcols = min(32, p.Nc - col);                // 32, or 16 for the last block
         {
-          float v[16], w[16];
-          tmem_ld16(taddr + (uint32_t)col, v);
-          tmem_ld16(taddr + (uint32_t)(p.Nc + col), w);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) stg[lane * 33 + j] = v[j] + w[j];
+          uint32_t v[32], w[32];                              // main and correction accumulators of this row
           if (wcols > 16) {
-            tmem_ld16(taddr + (uint32_t)col + 16, v);
-            tmem_ld16(taddr + (uint32_t)(p.Nc + col) + 16, w);
+            tmem_ld32_nowait(taddr + (uint32_t)col, v);
+            tmem_ld32_nowait(taddr + (uint32_t)(p.Nc + col), w);
+            tmem_ld_wait();
+          } else {
+            float a[16], b[16];
+            tmem_ld16(taddr + (uint32_t)col, a);
+            tmem_ld16(taddr + (uint32_t)(p.Nc + col), b);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) stg[lane * 33 + 16 + j] = v[j] + w[j];
+            for (int j = 0; j < 16; ++j) { v[j] = __float_as_uint(a[j]); w[j] = __float_as_uint(b[j]); v[16 + j] = 0; w[16 + j] = 0; }
           }
+          float4* srow = reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            srow[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]),
+                                  __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]),
+                                  __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]));
         }
         __syncwarp();
         const int nb = chunk_n0 + col;                        // first global column of the block
-        if (vec) {
+        if (vec || dense) {
+          // lane = 4 consecutive columns of rows vr, vr+4, ..., vr+28
           const int n = nb + vc;
           if (vc < wcols && n < N) {
             const float4 bia = c.bias ? __ldg(reinterpret_cast<const float4*>(c.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
+            const float* sp = stg + vr * TC_EPI_PITCH + vc;
+            float4 o[8];
+#pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int r = vr + 4 * it;
-              const int m = mw + r;
-              if (m < M) {
-                const float* sp = stg + r * 33 + vc;
-                float4 o = make_float4(sp[0] + bia.x, sp[1] + bia.y, sp[2] + bia.z, sp[3] + bia.w);
-                if (c.res) {
-                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(c.res + (size_t)m * N + n));
-                  o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
-                }
-                if (c.up) {
-                  const int b = m / hw, rem = m - b * hw;
-                  const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
-                  const size_t uo = (((size_t)b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N;
-                  const float4 t4 = __ldg(reinterpret_cast<const float4*>(c.up + uo + n));
-                  o.x += t4.x; o.y += t4.y; o.z += t4.z; o.w += t4.w;
-                }
-                if (c.act) o = act4(o, c.act);
-                *reinterpret_cast<float4*>(c.out + (size_t)m * N + n) = o;
+              o[it] = *reinterpret_cast<const float4*>(sp + it * 4 * TC_EPI_PITCH);
+              o[it].x += bia.x; o[it].y += bia.y; o[it].z += bia.z; o[it].w += bia.w;
+            }
+            if (c.res) {          // all 8 loads are issued before the first use (rows past M are clamped, never stored)
+              float4 t[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int m = mw + min(vr + 4 * it, rows_ok - 1);
+                t[it] = __ldg(reinterpret_cast<const float4*>(c.res + (size_t)m * N + n));
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) { o[it].x += t[it].x; o[it].y += t[it].y; o[it].z += t[it].z; o[it].w += t[it].w; }
+            }
+            if (c.up) {
+              float4 t[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) t[it] = __ldg(reinterpret_cast<const float4*>(c.up + up_off[it] + n));
+#pragma unroll
+              for (int it = 0; it < 8; ++it) { o[it].x += t[it].x; o[it].y += t[it].y; o[it].z += t[it].z; o[it].w += t[it].w; }
+            }
+            if (c.act == YL_ACT_RELU) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                o[it].x = fmaxf(o[it].x, 0.f); o[it].y = fmaxf(o[it].y, 0.f); o[it].z = fmaxf(o[it].z, 0.f); o[it].w = fmaxf(o[it].w, 0.f);
+              }
+            } else if (c.act) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it) o[it] = act4(o[it], c.act);
+            }
+            if (!dense) {
+              float* optr = c.out + (size_t)(mw + vr) * N + n;
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                if (vr + 4 * it < rows_ok) *reinterpret_cast<float4*>(optr + (size_t)it * 4 * N) = o[it];
+            } else {
+              float* dp = dstg + vr * N + (n - chunk_n0);
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                float* d = dp + it * 4 * N;
+                d[0] = o[it].x;
+                if (n + 1 < N) d[1] = o[it].y;
+                if (n + 2 < N) d[2] = o[it].z;
+                if (n + 3 < N) d[3] = o[it].w;
               }
             }
           }
         } else {
-          const int n = nb + lane;                            // scalar path: lane = column, one row per instruction
+          const int n = nb + lane;                            // generic path (anchors > 1 ...): lane = column
           if (lane < wcols && n < N) {
             const float bia = c.bias ? __ldg(c.bias + n) : 0.f;
             const int a = n / D, dd = n - a * D;
-            for (int r = 0; r < 32; ++r) {
+            for (int r = 0; r < rows_ok; ++r) {
               const int m = mw + r;
-              if (m >= M) break;
-              float o = stg[r * 33 + lane] + bia;
+              float o = stg[r * TC_EPI_PITCH + lane] + bia;
               if (c.res) o += __ldg(c.res + (size_t)m * N + n);
               size_t oidx = (size_t)m * N + n;
               if (c.up || c.anchors > 1) {
@@ -391,7 +540,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+      if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));     // TMEM is drained: the MMA warp may reuse it
+      if (dense) {
+        // rows of a warp are consecutive in memory ([M][N] row-major, one chunk): write them as one 16 B-aligned span
+        float* dst = c.out + (size_t)mw * N;
+        const int tot = rows_ok * N, tot4 = tot >> 2;
+        for (int i = lane; i < tot4; i += 32)
+          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(dstg)[i];
+        for (int i = (tot4 << 2) + lane; i < tot; i += 32) dst[i] = dstg[i];
+        __syncwarp();
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -408,7 +566,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 // ---- host side -----------------------------------------------------------------------------------
 // Decide whether (K, N) fits the resident-weight design and how N is chunked.  Shared with the packer through
 // the image layout only ([2][nslab][Npad][32]), which does not depend on the chunking.
-bool tc_plan(int K, int N, int* Nc_out, int* nchunks_out, int* stages_out) {
+static bool tc_dense_epi(int N, int anchors, int Nc, int nchunks) { return (N & 3) != 0 && anchors <= 1 && nchunks == 1 && Nc <= 128; }
+
+bool tc_plan(int K, int N, int anchors, int* Nc_out, int* nchunks_out, int* stages_out) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
   const int Npad = (N + 15) / 16 * 16;
@@ -416,7 +576,8 @@ bool tc_plan(int K, int N, int* Nc_out, int* nchunks_out, int* stages_out) {
     int Nc = ((Npad / 16 + nch - 1) / nch) * 16;
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
     const size_t wbytes = (size_t)2 * nslab * Nc * 128;
-    const size_t fixed = wbytes + TC_AUX_BYTES + 1024;
+    const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
+    const size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
     if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
     int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -431,18 +592,23 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.c = c;
   p.wimg = wimg;
   p.mode = mode;
+  static const int raw_hi_env = [] { const char* e = getenv("YL_TC_RAWHI"); return e ? atoi(e) : 1; }();
+  p.raw_hi = raw_hi_env;
   p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
-  YL_REQUIRE(tc_plan(p.K, c.Cout, &p.Nc, &p.nchunks, &p.stages), "shape does not fit the tcgen05 conv kernel");
+  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, &p.Nc, &p.nchunks, &p.stages), "shape does not fit the tcgen05 conv kernel");
+  p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE(mode != 3 && (c.Cin & 3) == 0, "tcgen05 conv needs NHWC input with Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
   p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
   YL_REQUIRE(p.M < (1ll << 31) - TC_BM, "too many output pixels for 32-bit row indices");
+  YL_REQUIRE(!c.up || (long long)c.B * c.Hu * c.Wu * c.Cout < (1ll << 31), "upsample source too large for 32-bit offsets");
   int cols = 32;
   while (cols < 4 * p.Nc) cols <<= 1;
   p.tmem_cols = cols;
-  const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES + 1024;
+  const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES +
+                      (p.dense_epi ? (size_t)4 * 32 * p.Nc * 4 : 0) + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
