@@ -39,7 +39,7 @@ struct yl_engine {
 namespace yl {
 
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
-bool tc_plan(int K, int N, int anchors, int* Nc, int* nchunks, int* stages);
+bool tc_plan(int K, int N, int anchors, int mode, int* Nc, int* nchunks, int* stages, int* halo_slots);
 
 static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
                   int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st) {
@@ -59,11 +59,11 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {
     const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
     const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
-    int nc, nch, stg;
+    int nc, nch, stg, hs;
     // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
     // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
     const bool big = (K >= 32 && op.cout >= 32) || use_tc == 2;
-    if (big && tc_plan(K, op.cout, op.anchors, &nc, &nch, &stg) && (op.cin & 3) == 0)
+    if (big && tc_plan(K, op.cout, op.anchors, mode, &nc, &nch, &stg, &hs) && (op.cin & 3) == 0)
     { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
   }
   ++g_simt_launches;

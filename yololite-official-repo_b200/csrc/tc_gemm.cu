@@ -31,16 +31,21 @@ constexpr int TC_MMA_WARP = 12;
 constexpr int TC_THREADS = 32 * 13;
 constexpr int TC_BM = 128;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one K-slab (32 fp32) of the A tile
-constexpr int TC_SMEM_BUDGET = 224 * 1024;
+constexpr int TC_SMEM_BUDGET = 226 * 1024;      // of the 227 KB a CTA may use
 constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // MODE 2 spatial tile = 128 output pixels
+constexpr int TC_HALO_W = TC_TILE_W + 2, TC_HALO_PIX = (TC_TILE_H + 2) * (TC_TILE_W + 2);
+constexpr int TC_HALO_BYTES = TC_HALO_PIX * 128;     // one 32-channel slab of the halo tile
 constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
-constexpr int TC_AUX_BYTES = 256 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
+constexpr int TC_AUX_BYTES = 128 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
 
 struct TcParams {
   ConvParams c;
   const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
   int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise3x3->pointwise
   int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
+  int tiles_x, tiles_y; // MODE 2: spatial tiles (8 rows x 16 cols of output pixels) per image
+  int halo_slots;       // MODE 2: halo ring depth
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
   int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
   long long M;
@@ -176,7 +181,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
   unsigned char* w_hi = smem;
   unsigned char* w_lo = w_hi + (size_t)p.nslab * w_slab_bytes;
   unsigned char* a_ring = w_lo + (size_t)p.nslab * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES);
+  unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x 23 KB
+  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES : 0));   // [9][nslab*32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)9 * p.nslab * 32 * 4 : 0));
   uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
   uint64_t* empty_bar = bars + TC_MAX_STAGES;      // [stages]   MMA commit -> producers (count 1)
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
@@ -206,6 +213,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       if (chunk_n0 + (r >> 3) < p.Npad)
         v = __ldg(reinterpret_cast<const float4*>(p.wimg) + ((size_t)ps * p.Npad + chunk_n0) * 8 + r);
       reinterpret_cast<float4*>(w_hi)[(size_t)ps * per_slab4 + r] = v;
+    }
+  }
+  if (MODE == 2) {
+    const int cp = p.nslab * 32;
+    for (int i = threadIdx.x; i < 9 * cp; i += TC_THREADS) {
+      const int tap = i / cp, k = i - tap * cp;
+      w2s[i] = k < p.K ? __ldg(c.w2 + tap * c.Cin + k) : 0.f;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -322,43 +336,81 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
         if (++c_stage == p.stages) c_stage = 0;
       }
     } else {
-      // fused DWConvBlock: the depthwise 3x3 is computed in registers while loading (one K-slab per round)
-      int stage = 0;
+      // fused DWConvBlock on spatial tiles of 8x16 output pixels.  Per K-slab the (8+2)x(16+2) halo of the INPUT is copied
+      // with cp.async into a small ring (zero-filled outside the image = the conv padding); after a producer-group
+      // barrier every thread computes the depthwise 3x3 for 4 horizontally adjacent pixels x 4 channels from shared
+      // memory (18 halo + 9 weight 16 B loads for 4 outputs), splits hi/lo and writes the A stage.
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = my_tiles * p.nslab;
+      const int HS = p.halo_slots;
+      const int per_img = p.tiles_x * p.tiles_y;
+      const int g = t >> 3, ty = g >> 2, tx0 = (g & 3) * 4;
+      const int cp = p.nslab * 32;
+      int issued = 0, i_tile = blockIdx.x, i_s = 0, i_slot = 0;
+      auto issue = [&]() {
+        if (issued < total) {
+          const int b = i_tile / per_img, rem = i_tile - b * per_img;
+          const int y0 = (rem / p.tiles_x) * TC_TILE_H - 1, x0 = (rem % p.tiles_x) * TC_TILE_W - 1;
+          const uint32_t dst = smem_u32(halo) + (uint32_t)i_slot * TC_HALO_BYTES;
+          const float* img = c.in + (size_t)b * c.Hin * c.Win * c.Cin + i_s * 32;
+          for (int idx = t; idx < TC_HALO_PIX * 8; idx += 256) {
+            const int pix = idx >> 3, hc = idx & 7;
+            const int hy = pix / TC_HALO_W, hx = pix - hy * TC_HALO_W;
+            const int y = y0 + hy, x = x0 + hx;
+            const float* src = c.in;
+            uint32_t nbytes = 0;
+            if (y >= 0 && y < c.Hin && x >= 0 && x < c.Win && i_s * 32 + hc * 4 < p.K) {
+              src = img + ((size_t)y * c.Win + x) * c.Cin + hc * 4;
+              nbytes = 16;
+            }
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)idx * 16u), "l"(src), "r"(nbytes) : "memory");
+          }
+          if (++i_s == p.nslab) { i_s = 0; i_tile += gridDim.x; }
+          if (++i_slot == HS) i_slot = 0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");      // always commit: keeps the group count uniform
+        ++issued;
+      };
+      for (int j = 0; j < HS - 1; ++j) issue();
+      int stage = 0, c_slot = 0, c_s = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = tile * TC_BM;
-        const float* rbase[4];
-        int roy[4], rox[4];
-        bool rok[4];
+      for (int j = 0; j < total; ++j) {
+        if (HS == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // item j landed for everyone; slot of item j-1 is free
+        issue();                                                  // item j + HS - 1
+        const unsigned char* hb = halo + (size_t)c_slot * TC_HALO_BYTES + ((size_t)(ty * TC_HALO_W + tx0) * 8 + ch) * 16;
+        const float* wk = w2s + c_s * 32 + ch * 4;
+        float4 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int m = m0 + r0 + 32 * i;
-          rok[i] = m < M;
-          const int mm = rok[i] ? m : 0;
-          const int hw = c.Wout * c.Hout;
-          const int b = mm / hw, rem = mm - b * hw;
-          const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
-          rbase[i] = c.in + (size_t)b * c.Hin * c.Win * c.Cin;
-          roy[i] = oy * c.stride - c.pad;
-          rox[i] = ox * c.stride - c.pad;
+        for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          float4 h[6];
+#pragma unroll
+          for (int x = 0; x < 6; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(ky * TC_HALO_W + x) * 128);
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + (ky * 3 + kx) * cp);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              a[i].x = fmaf(h[i + kx].x, w4.x, a[i].x); a[i].y = fmaf(h[i + kx].y, w4.y, a[i].y);
+              a[i].z = fmaf(h[i + kx].z, w4.z, a[i].z); a[i].w = fmaf(h[i + kx].w, w4.w, a[i].w);
+            }
+          }
         }
-        for (int s = 0; s < p.nslab; ++s) {
-          const int k = s * 32 + ch * 4;
-          float4 v[4];
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            v[i] = (k < p.K && rok[i]) ? load_a<2>(c, rbase[i], roy[i], rox[i], k, 0, 0, k) : make_float4(0.f, 0.f, 0.f, 0.f);
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-          unsigned char* lo = hi + TC_SLAB_BYTES;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) split_store(hi, lo, r0 + 32 * i, ch, v[i]);
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
+        for (int i = 0; i < 4; ++i) split_store(hi, hi + TC_SLAB_BYTES, ty * TC_TILE_W + tx0 + i, ch, a[i]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++c_slot == HS) c_slot = 0;
+        if (++c_s == p.nslab) c_s = 0;
       }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
   } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ===============================
@@ -417,8 +469,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      const int mw = tile * TC_BM + q * 32;                   // first row of this warp
-      const int rows_ok = min(32, M - mw);                    // rows of this warp inside the matrix
+      const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
+      const int rows_ok = MODE == 2 ? 32 : min(32, M - mw);   // rows of this warp inside the matrix
+      // element offset of the output row for each of the 8 rows this lane owns, -1 = outside
+      int orow[8];
+      if (MODE == 2) {
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int b = tile / per_img, rem = tile - b * per_img;
+        const int y0 = (rem / p.tiles_x) * TC_TILE_H, x0 = (rem % p.tiles_x) * TC_TILE_W;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = q * 32 + vr + 4 * it;
+          const int y = y0 + (r >> 4), x = x0 + (r & 15);
+          orow[it] = (y < c.Hout && x < c.Wout) ? ((b * c.Hout + y) * c.Wout + x) * N : -1;
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) orow[it] = (vr + 4 * it < rows_ok) ? (mw + vr + 4 * it) * N : -1;
+      }
       // element offsets of the nearest-upsample source row for the 8 rows this lane owns (one division per tile)
       int up_off[8];
       if (c.up && (vec || dense)) {
@@ -476,8 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
               float4 t[8];
 #pragma unroll
               for (int it = 0; it < 8; ++it) {
-                const int m = mw + min(vr + 4 * it, rows_ok - 1);
-                t[it] = __ldg(reinterpret_cast<const float4*>(c.res + (size_t)m * N + n));
+                t[it] = __ldg(reinterpret_cast<const float4*>(c.res + max(orow[it], 0) + n));
               }
 #pragma unroll
               for (int it = 0; it < 8; ++it) { o[it].x += t[it].x; o[it].y += t[it].y; o[it].z += t[it].z; o[it].w += t[it].w; }
@@ -499,10 +566,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
               for (int it = 0; it < 8; ++it) o[it] = act4(o[it], c.act);
             }
             if (!dense) {
-              float* optr = c.out + (size_t)(mw + vr) * N + n;
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                if (vr + 4 * it < rows_ok) *reinterpret_cast<float4*>(optr + (size_t)it * 4 * N) = o[it];
+                if (orow[it] >= 0) *reinterpret_cast<float4*>(c.out + orow[it] + n) = o[it];
             } else {
               float* dp = dstg + vr * N + (n - chunk_n0);
 #pragma unroll
@@ -568,7 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 // the image layout only ([2][nslab][Npad][32]), which does not depend on the chunking.
 static bool tc_dense_epi(int N, int anchors, int Nc, int nchunks) { return (N & 3) != 0 && anchors <= 1 && nchunks == 1 && Nc <= 128; }
 
-bool tc_plan(int K, int N, int anchors, int* Nc_out, int* nchunks_out, int* stages_out) {
+bool tc_plan(int K, int N, int anchors, int mode, int* Nc_out, int* nchunks_out, int* stages_out, int* halo_slots_out) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
   const int Npad = (N + 15) / 16 * 16;
@@ -577,11 +643,19 @@ bool tc_plan(int K, int N, int anchors, int* Nc_out, int* nchunks_out, int* stag
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
     const size_t wbytes = (size_t)2 * nslab * Nc * 128;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
-    const size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
+    size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
+    int halo_slots = 0;
+    if (mode == 2) {                             // halo ring (2..3 slots) + depthwise weights, 2 A stages
+      fixed += (size_t)9 * nslab * 32 * 4 + 2 * 2 * TC_SLAB_BYTES;
+      if (fixed + 2 * TC_HALO_BYTES > (size_t)TC_SMEM_BUDGET) continue;
+      halo_slots = (fixed + 3 * TC_HALO_BYTES <= (size_t)TC_SMEM_BUDGET) ? 3 : 2;
+      *Nc_out = Nc; *nchunks_out = nch; *stages_out = 2; *halo_slots_out = halo_slots;
+      return true;
+    }
     if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
     int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    *Nc_out = Nc; *nchunks_out = nch; *stages_out = stages;
+    *Nc_out = Nc; *nchunks_out = nch; *stages_out = stages; *halo_slots_out = 0;
     return true;
   }
   return false;
@@ -597,23 +671,31 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
-  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, &p.Nc, &p.nchunks, &p.stages), "shape does not fit the tcgen05 conv kernel");
+  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, &p.Nc, &p.nchunks, &p.stages, &p.halo_slots), "shape does not fit the tcgen05 conv kernel");
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE(mode != 3 && (c.Cin & 3) == 0, "tcgen05 conv needs NHWC input with Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
   p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
+  if (mode == 2) {
+    YL_REQUIRE(!c.res && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0, "fused DWConvBlock epilogue takes no residual/upsample/head layout");
+    p.tiles_x = (c.Wout + TC_TILE_W - 1) / TC_TILE_W;
+    p.tiles_y = (c.Hout + TC_TILE_H - 1) / TC_TILE_H;
+    p.num_tiles = c.B * p.tiles_x * p.tiles_y;
+  }
+  YL_REQUIRE(p.M * c.Cout < (1ll << 31), "output too large for 32-bit element offsets");
   YL_REQUIRE(p.M < (1ll << 31) - TC_BM, "too many output pixels for 32-bit row indices");
   YL_REQUIRE(!c.up || (long long)c.B * c.Hu * c.Wu * c.Cout < (1ll << 31), "upsample source too large for 32-bit offsets");
   int cols = 32;
   while (cols < 4 * p.Nc) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES +
-                      (p.dense_epi ? (size_t)4 * 32 * p.Nc * 4 : 0) + 1024;
+                      (p.dense_epi ? (size_t)4 * 32 * p.Nc * 4 : 0) +
+                      (mode == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES + (size_t)9 * p.nslab * 32 * 4 : 0) + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BUDGET + 2048));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int gx = sm_count / p.nchunks;
