@@ -283,7 +283,7 @@ def run_b200(a):
     torch.cuda.synchronize(dev)
     post_ms = p0.elapsed_time(p1) / reps
     fwd_ms = float(acc.sum())
-    kinds = {0: "stem_kernel", 1: "conv_gemm_kernel", 2: "dw_kernel", 3: "conv_gemm_kernel<dwpw>"}
+    kinds = {0: "stem_kernel", 1: "conv", 2: "dw_kernel", 3: "dwpw", 4: "stem+conv3x3s2"}
     # spatial sizes per op for the byte model
     per_op = []
     hw = {}
@@ -292,7 +292,10 @@ def run_b200(a):
         return (h + 2 * (k // 2) - k) // s + 1, (w + 2 * (k // 2) - k) // s + 1
     for i, op in enumerate(eng.program.ops):
         hin, win = (S, S) if op["src"] < 0 else hw[op["src"]]
-        ho, wo = out_hw(hin, win, op["k"], op["stride"])
+        if op["kind"] == 4:
+            ho, wo = out_hw(*out_hw(hin, win, 3, 2), op["k"], op["stride"])
+        else:
+            ho, wo = out_hw(hin, win, op["k"], op["stride"])
         if op["dst"] >= 0:
             hw[op["dst"]] = (ho, wo)
         wbytes = 4 * (op["k"] * op["k"] * op["cin"] * op["cout"] + op["cout"] + (9 * op["cin"] if op["kind"] == 3 else 0))
@@ -303,7 +306,12 @@ def run_b200(a):
             nbytes += 4 * B * ho * wo * op["cout"]
         if op["up"] >= 0:
             nbytes += 4 * B * (ho // 2) * (wo // 2) * op["cout"]
-        per_op.append((kinds[op["kind"]], i, nbytes, acc[i], op))
+        name = kinds[op["kind"]]
+        if op["kind"] in (1, 3, 4):
+            kk = op["cin"] if op["kind"] == 3 or op["k"] == 1 else op["k"] * op["k"] * (32 if op["kind"] == 4 else op["cin"])
+            on_tc = (not a.no_tc) and op["wt_off"] >= 0 and (op["kind"] == 4 or (kk >= 32 and op["cout"] >= 32))
+            name = ("tc_conv_kernel<" if on_tc else "conv_gemm_kernel<") + name + ">"
+        per_op.append((name, i, nbytes, acc[i], op))
     cand = [(t, name, i, nb) for (name, i, nb, t, op) in per_op]
     cand.append((post_ms, "post_kernel", -1, 4 * B * N * (5 + a.nc)))
     t_top, name_top, i_top, nb_top = max(cand)

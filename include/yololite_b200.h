@@ -37,8 +37,12 @@ enum yl_op_kind {
   YL_OP_CONV = 1,  /* dense KxK conv as implicit GEMM, NHWC -> NHWC; K=1 is the pointwise conv; epilogue:
                       +bias, +residual buffer, +nearest-upsampled coarser buffer, act, head layout       */
   YL_OP_DW = 2,    /* depthwise KxK conv (K = 3 or 5), NHWC, +bias, act                                   */
-  YL_OP_DWPW = 3   /* fused DWConvBlock: depthwise 3x3 s1 (no bias) -> pointwise + bias + act
+  YL_OP_DWPW = 3,  /* fused DWConvBlock: depthwise 3x3 s1 (no bias) -> pointwise + bias + act
                       (model_v2.py:23-39); the depthwise result never leaves shared memory               */
+  YL_OP_STEM2 = 4  /* fused conv_stem (3x3 s2, Cin=3, NCHW input, 32 ch, +bias+ReLU) -> dense 3x3 s2 conv + bias + act
+                      (timm blocks.0.0): the stem activation (13 MB/image at 640 px) never leaves shared memory.
+                      cin = 3, cout = channels of the second conv, k/stride/act = the second conv's, k2 = stem
+                      channels (32), w2_off = [27][32] stem weights followed by 32 stem biases, wt_off required  */
 };
 enum yl_act { YL_ACT_NONE = 0, YL_ACT_RELU = 1, YL_ACT_SILU = 2 };
 

@@ -15,7 +15,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yololite_b200 import _lib as L, packer  # noqa: E402
 
-KINDS = {"stem": 0, "conv": 1, "dw": 2, "dwpw": 3}
+KINDS = {"stem": 0, "conv": 1, "dw": 2, "dwpw": 3, "stem2": 4}
 
 
 def build(kind, cin, cout, k, stride, act, up, res):
@@ -40,6 +40,14 @@ def build(kind, cin, cout, k, stride, act, up, res):
         op.w_off = add(g.randn(k * k, cin) / k)
     elif kind == "stem":
         op.w_off = add(g.randn(27, cout) / 5)
+    elif kind == "stem2":
+        op.cin, op.k, op.stride, op.k2, op.src = 3, 3, 2, 32, -1
+        wm = np.zeros((288, (cout + 3) // 4 * 4))
+        wm[:, :cout] = g.randn(288, cout) / 17
+        op.w_off = add(wm)
+        op.wt_off = add(packer.tc_image(wm, cout))
+        wsm = g.randn(27, 32) / 5
+        op.w2_off = add(np.concatenate([wsm.reshape(-1), g.randn(32) * 0.3, packer.tc_image(wsm, 32).astype(np.float64)]))
     else:
         kk = 1 if kind == "dwpw" else k
         wm = np.zeros((kk * kk * cin, (cout + 3) // 4 * 4))
@@ -73,7 +81,9 @@ def main():
     B, H = a.batch, a.hw
     k = op.k
     ho = (H + 2 * (k // 2) - k) // a.stride + 1
-    x = torch.randn((B, 3, H, H) if a.kind == "stem" else (B, H, H, a.cin), device="cuda")
+    if a.kind == "stem2":
+        ho = ((H + 2 - 3) // 2 + 1 + 2 - 3) // 2 + 1
+    x = torch.randn((B, 3, H, H) if a.kind in ("stem", "stem2") else (B, H, H, a.cin), device="cuda")
     out = torch.empty((B, ho, ho, a.cout), device="cuda")
     res = torch.randn_like(out) if a.res else None
     up = torch.randn((B, (ho + 1) // 2, (ho + 1) // 2, a.cout), device="cuda") if a.up else None

@@ -14,5 +14,6 @@ YL_TC_RAWHI=$raw python scripts/bench_op.py --kind dwpw --cin 96 --cout 96 --hw 
 YL_TC_RAWHI=$raw python scripts/bench_op.py --kind dwpw --cin 96 --cout 96 --hw 40 --tc 1
 YL_TC_RAWHI=$raw python scripts/bench_op.py --kind dwpw --cin 96 --cout 96 --hw 20 --tc 1
 YL_TC_RAWHI=$raw python scripts/bench_op.py --kind conv --cin 16 --cout 48 --k 3 --stride 2 --hw 160 --tc 1
+YL_TC_RAWHI=$raw python scripts/bench_op.py --kind stem2 --cin 3 --cout 16 --k 3 --stride 2 --hw 640 --tc 1
 YL_TC_RAWHI=$raw python scripts/bench_op.py --kind conv --cin 96 --cout 85 --hw 80 --tc 1 --act 0
 done 2>&1 | tee gpurun_out/bench_ops.log

@@ -22,7 +22,15 @@ def run_program(P, x):
         src = x if op["src"] < 0 else bufs[op["src"]]          # NCHW tensors inside the interpreter
         assert src.shape[1] == cin, (op, src.shape)
         bias = None if op["b_off"] < 0 else blob[op["b_off"]:op["b_off"] + cout]
-        if op["kind"] == 0:
+        if op["kind"] == 4:       # fused stem (3x3 s2, 32 ch, ReLU) -> 3x3 s2 conv
+            sc = op["k2"]
+            ws = blob[op["w2_off"]:op["w2_off"] + 27 * sc].reshape(3, 3, 3, sc).permute(3, 2, 0, 1)
+            bs = blob[op["w2_off"] + 27 * sc:op["w2_off"] + 28 * sc]
+            mid = F.relu(F.conv2d(src, ws, bs, stride=2, padding=1))
+            ld = (cout + 3) // 4 * 4
+            w = blob[op["w_off"]:op["w_off"] + 9 * sc * ld].reshape(9 * sc, ld)[:, :cout].reshape(3, 3, sc, cout).permute(3, 2, 0, 1)
+            y = F.conv2d(mid, w, bias, stride=s, padding=1)
+        elif op["kind"] == 0:
             w = blob[op["w_off"]:op["w_off"] + k * k * cin * cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1)
             y = F.conv2d(src, w, bias, stride=s, padding=k // 2)
         elif op["kind"] in (1, 3):

@@ -180,3 +180,44 @@ def test_tensor_core_path_is_not_single_pass_tf32():
     n1 = L.lib().yl_stat(b"simt_launches")
     _run(1, x, w, None, 1, 1, 0, use_tc=0)
     assert L.lib().yl_stat(b"simt_launches") == n1 + 1
+
+
+@pytest.mark.parametrize("hw,n2", [((64, 64), 16), ((45, 52), 16), ((83, 38), 32), ((640, 640), 16)])
+def test_fused_stem_conv(hw, n2):
+    """YL_OP_STEM2: conv_stem (3x3 s2, 3->32, ReLU) -> 3x3 s2 conv (32->n2, ReLU) in one tcgen05 kernel."""
+    from yololite_b200 import _lib as L, packer
+    g = torch.Generator().manual_seed(hw[0] + n2)
+    B = 2 if hw[0] < 600 else 1
+    x = torch.randn(B, 3, hw[0], hw[1], generator=g)
+    ws = torch.randn(32, 3, 3, 3, generator=g) / 5
+    bs = torch.randn(32, generator=g) * 0.3
+    w2 = torch.randn(n2, 32, 3, 3, generator=g) / 17
+    b2 = torch.randn(n2, generator=g)
+    blob, off = [], [0]
+
+    def add(a):
+        a = np.ascontiguousarray(a, np.float32).reshape(-1)
+        o = off[0]
+        blob.append(a)
+        pad = (-a.size) % 64
+        if pad:
+            blob.append(np.zeros(pad, np.float32))
+        off[0] += a.size + pad
+        return o
+    op = L.YlOp()
+    op.kind, op.k, op.stride, op.act, op.anchors, op.k2 = L.OP_STEM2, 3, 2, 1, 0, 32
+    op.src, op.dst, op.res, op.up = -1, 1, -1, -1
+    op.cin, op.cout = 3, n2
+    wm = packer._gemm_w(w2.double().numpy())
+    op.w_off = add(wm)
+    op.wt_off = add(packer.tc_image(wm, n2))
+    wsm = np.transpose(ws.double().numpy(), (2, 3, 1, 0)).reshape(27, 32)
+    op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(wsm, 32).astype(np.float64)]))
+    op.b_off = add(packer._pad4(b2.double().numpy()))
+    dblob = torch.from_numpy(np.concatenate(blob)).cuda()
+    want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()
+    out = torch.full(want.shape, float("nan"), device="cuda")
+    xc = x.cuda()
+    L.check(L.lib().yl_run_op(ctypes.byref(op), dblob.data_ptr(), xc.data_ptr(), None, None, out.data_ptr(), B, hw[0], hw[1], 0, 0, 1, None))
+    torch.cuda.synchronize()
+    assert float((out.cpu() - want).abs().max()) <= TOL

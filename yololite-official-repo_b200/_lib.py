@@ -15,7 +15,7 @@ class YlOp(ctypes.Structure):
                 ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64)]
 
 
-OP_STEM, OP_CONV, OP_DW, OP_DWPW = 0, 1, 2, 3
+OP_STEM, OP_CONV, OP_DW, OP_DWPW, OP_STEM2 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 SRC_INPUT = -1
 

@@ -56,6 +56,11 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   p.Hu = hu; p.Wu = wu;
   p.act = op.act; p.anchors = op.anchors;
   if (op.kind == YL_OP_DWPW) { p.KS = op.k2; p.pad = op.k2 / 2; }     // geometry of the depthwise stage
+  if (op.kind == YL_OP_STEM2) {
+    p.Cin = op.k2;                                // K of the second conv = 9 * stem channels
+    ++g_tc_launches;
+    return launch_tc_conv(p, blob + op.wt_off, 3, sm_count, st);
+  }
   if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {
     const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
     const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
@@ -96,9 +101,14 @@ static int plan(yl_engine* e, int B, int H, int W) {
     }
     YL_REQUIRE(cin == op.cin, "op.cin does not match the source buffer");
     const int pad = op.k / 2;
+    if (op.kind == YL_OP_STEM2) {                 // two stacked 3x3 s2 convs: size after the stem first
+      hin = (hin + 2 - 3) / 2 + 1; win = (win + 2 - 3) / 2 + 1;
+      YL_REQUIRE(hin >= 1 && win >= 1, "input too small for the network");
+    }
     const int hout = (hin + 2 * pad - op.k) / op.stride + 1;
     const int wout = (win + 2 * pad - op.k) / op.stride + 1;
     YL_REQUIRE(hout >= 1 && wout >= 1, "input too small for the network");
+    if (op.kind == YL_OP_STEM2) { hin = H; win = W; }
     e->op_hin[i] = hin; e->op_win[i] = win; e->op_hout[i] = hout; e->op_wout[i] = wout;
     if (op.dst >= 0) {
       YL_REQUIRE(op.dst < e->n_buffers, "op.dst out of range");
@@ -164,7 +174,9 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
   YL_REQUIRE(prop.major == 10, "yololite_b200 is built for sm_100a (B200) only");
   for (int i = 0; i < n_ops; ++i) {
     const yl_op& op = ops[i];
-    YL_REQUIRE(op.kind >= YL_OP_STEM && op.kind <= YL_OP_DWPW, "unknown op kind");
+    YL_REQUIRE(op.kind >= YL_OP_STEM && op.kind <= YL_OP_STEM2, "unknown op kind");
+    YL_REQUIRE(op.kind != YL_OP_STEM2 || (op.wt_off >= 0 && op.w2_off >= 0 && op.k2 == 32 && op.k == 3 && op.stride == 2),
+               "YL_OP_STEM2 needs the tcgen05 weight image, stem weights, 32 stem channels and a 3x3 s2 second conv");
     YL_REQUIRE(op.k >= 1 && (op.k & 1) && op.stride >= 1 && op.cin >= 1 && op.cout >= 1, "bad conv geometry");
     YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
     YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
@@ -213,7 +225,9 @@ int yl_run_op(const yl_op* op, const float* blob_dev, const float* in, const flo
   int sms = 0;
   YL_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const int pad = op->k / 2;
-  const int hout = (Hin + 2 * pad - op->k) / op->stride + 1, wout = (Win + 2 * pad - op->k) / op->stride + 1;
+  int hs = Hin, ws = Win;
+  if (op->kind == YL_OP_STEM2) { hs = (Hin + 2 - 3) / 2 + 1; ws = (Win + 2 - 3) / 2 + 1; }
+  const int hout = (hs + 2 * pad - op->k) / op->stride + 1, wout = (ws + 2 * pad - op->k) / op->stride + 1;
   return run_op(*op, blob_dev, in, res, up, out, B, Hin, Win, hout, wout, Hu, Wu, use_tensor_cores, sms,
                 reinterpret_cast<cudaStream_t>(stream));
 }

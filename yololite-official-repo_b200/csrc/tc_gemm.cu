@@ -36,6 +36,12 @@ constexpr int TC_MAX_STAGES = 4;
 constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // MODE 2 spatial tile = 128 output pixels
 constexpr int TC_HALO_W = TC_TILE_W + 2, TC_HALO_PIX = (TC_TILE_H + 2) * (TC_TILE_W + 2);
 constexpr int TC_HALO_BYTES = TC_HALO_PIX * 128;     // one 32-channel slab of the halo tile
+// MODE 3 (stem 3x3 s2 on the NCHW input -> 3x3 s2 conv): per 8x16 output tile the stem output halo is 17x33 pixels x 32 ch,
+// computed from a 3 x 35 x 67 input patch
+constexpr int S3_HALO_H = 2 * TC_TILE_H + 1, S3_HALO_W = 2 * TC_TILE_W + 1, S3_HALO_PIX = S3_HALO_H * S3_HALO_W;
+constexpr int S3_PATCH_H = 2 * S3_HALO_H + 1, S3_PATCH_W = 2 * S3_HALO_W + 1, S3_PATCH_PITCH = 68;
+constexpr int S3_PATCH_BYTES = 3 * S3_PATCH_H * S3_PATCH_PITCH * 4;      // 28560
+constexpr int S3_HALO_BYTES = S3_HALO_PIX * 128;                        // 71808
 constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
 constexpr int TC_AUX_BYTES = 128 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
 
@@ -44,7 +50,8 @@ struct TcParams {
   const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
   int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise3x3->pointwise
   int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
-  int tiles_x, tiles_y; // MODE 2: spatial tiles (8 rows x 16 cols of output pixels) per image
+  int Hs, Ws;           // MODE 3: stem output size
+  int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
   int halo_slots;       // MODE 2: halo ring depth
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
   int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
@@ -182,13 +189,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
   unsigned char* w_lo = w_hi + (size_t)p.nslab * w_slab_bytes;
   unsigned char* a_ring = w_lo + (size_t)p.nslab * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
   unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x 23 KB
-  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES : 0));   // [9][nslab*32]
+  // MODE 3: `halo` region = stem weight image (hi 4 KB, lo 4 KB) | stem-output halo (71808 B) | input patch (28560 B)
+  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)9 * p.nslab * 32 * 4 : 0));
   uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
   uint64_t* empty_bar = bars + TC_MAX_STAGES;      // [stages]   MMA commit -> producers (count 1)
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA         (count 4)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* halo_full = tempty_bar + 2;            // MODE 3: epilogue (4 warps) -> producers: stem halo written
+  uint64_t* halo_empty = tempty_bar + 3;           // MODE 3: producers (8 warps) -> epilogue: halo consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
   float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 rows x TC_EPI_PITCH floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
@@ -196,6 +206,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), TC_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
+    mbar_init(smem_u32(halo_full), 4);
+    mbar_init(smem_u32(halo_empty), TC_PROD_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -214,6 +226,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
         v = __ldg(reinterpret_cast<const float4*>(p.wimg) + ((size_t)ps * p.Npad + chunk_n0) * 8 + r);
       reinterpret_cast<float4*>(w_hi)[(size_t)ps * per_slab4 + r] = v;
     }
+  }
+  if (MODE == 3) {   // stem weight image [2][32 rows][32 k], pre-swizzled, right after the 27x32 weights + 32 biases
+    for (int i = threadIdx.x; i < 512; i += TC_THREADS)
+      reinterpret_cast<float4*>(halo)[i] = __ldg(reinterpret_cast<const float4*>(c.w2 + 896) + i);
   }
   if (MODE == 2) {
     const int cp = p.nslab * 32;
@@ -234,7 +250,116 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
     // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
     const int ch = t & 7, r0 = t >> 3;
-    if (MODE != 2) {
+    if (MODE == 3) {
+      // Fused stem: per 8x16 output tile, conv_stem (3x3 s2, Cin=3, NCHW input) is itself run on the tensor cores as five
+      // 128-row GEMM tiles over the 17x33 halo of its output (A = im2col of a 3x35x67 input patch held in shared memory,
+      // K = 27 padded to 32, N = 32); the epilogue warps write bias+ReLU of those into a shared-memory halo (exactly zero
+      // outside the stem output = the second conv's padding); the 9 taps of the second 3x3 s2 conv are then 9 K-slabs
+      // gathered from that halo.  The 13 MB/image stem activation never exists in HBM.
+      unsigned char* halb = halo + 8192;
+      float* patch = reinterpret_cast<float*>(halb + S3_HALO_BYTES);
+      const int per_img = p.tiles_x * p.tiles_y;
+      const size_t plane = (size_t)c.Hin * c.Win;
+      const int pw = t >> 5;                          // producer warp 0..7
+      // this thread's 4 k's of the stem im2col row: k = 4*ch + q = (ky*3 + kx)*3 + ci
+      int poff[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = ch * 4 + q, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+        poff[q] = k < 27 ? (ci * S3_PATCH_H + ky) * S3_PATCH_PITCH + kx : -1;
+      }
+      auto issue_patch = [&](int tile) {
+        if (tile < tiles) {
+          const int b = tile / per_img, rem = tile - b * per_img;
+          const int iy0 = (rem / p.tiles_x) * TC_TILE_H * 4 - 3, ix0 = (rem % p.tiles_x) * TC_TILE_W * 4 - 3;
+          const float* img = c.in + (size_t)b * 3 * plane;
+          for (int row = pw; row < 3 * S3_PATCH_H; row += TC_PROD_WARPS) {      // row = ci*35 + pr
+            const int ci = row / S3_PATCH_H, iy = iy0 + row - ci * S3_PATCH_H;
+            const bool rok = iy >= 0 && iy < c.Hin;
+            const float* srow = img + ci * plane + (size_t)(rok ? iy : 0) * c.Win;
+            const uint32_t drow = smem_u32(patch + row * S3_PATCH_PITCH);
+#pragma unroll
+            for (int u = 0; u < 3; ++u) {
+              const int pc = lane + 32 * u;
+              if (pc < S3_PATCH_W) {
+                const int ix = ix0 + pc;
+                const bool ok = rok && ix >= 0 && ix < c.Win;
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + pc * 4), "l"(ok ? srow + ix : c.in),
+                             "r"(ok ? 4u : 0u) : "memory");
+              }
+            }
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      issue_patch(blockIdx.x);
+      int stage = 0;
+      uint32_t phase = 0, hphase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // patch landed for everyone
+        // ---- stem A tiles: 5 x 128 halo pixels, one K-slab each
+        for (int j = 0; j < 5; ++j) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = r0 + 32 * i, pix = j * 128 + row;
+            float e[4] = {0.f, 0.f, 0.f, 0.f};
+            if (pix < S3_HALO_PIX) {
+              const int hy = pix / S3_HALO_W, hx = pix - hy * S3_HALO_W;
+              const float* pb = patch + 2 * hy * S3_PATCH_PITCH + 2 * hx;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (poff[q] >= 0) e[q] = pb[poff[q]];
+            }
+            const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+            float4 l;
+            l.x = e[0] - __uint_as_float(__float_as_uint(e[0]) & 0xFFFFE000u);
+            l.y = e[1] - __uint_as_float(__float_as_uint(e[1]) & 0xFFFFE000u);
+            l.z = e[2] - __uint_as_float(__float_as_uint(e[2]) & 0xFFFFE000u);
+            l.w = e[3] - __uint_as_float(__float_as_uint(e[3]) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(hi + off) = make_float4(e[0], e[1], e[2], e[3]);
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + off) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");              // everyone is done reading the patch
+        issue_patch(tile + gridDim.x);
+        mbar_wait(smem_u32(halo_full), hphase);                     // the epilogue warps have written this tile's halo
+        hphase ^= 1;
+        // ---- the 9 taps = 9 K-slabs gathered from the halo (chunk c of pixel q sits at position c ^ (q & 7))
+        for (int s = 0; s < 9; ++s) {
+          const int ky = s / 3, kx = s - ky * 3;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = r0 + 32 * i, ty = row >> 4, tx = row & 15;
+            const int hp = (2 * ty + ky) * S3_HALO_W + 2 * tx + kx;
+            const float4 a = *reinterpret_cast<const float4*>(halb + (size_t)hp * 128 + ((ch ^ (hp & 7)) << 4));
+            const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+            float4 l;
+            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(hi + off) = a;                 // the tensor core drops the low 13 bits itself
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + off) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(halo_empty));           // this warp no longer reads the halo
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (MODE != 2) {
       // cp.async pipeline: the 16 B pieces are copied global -> shared (zero-filled outside the image / past K) straight
       // into their swizzled slot of the stage's `hi` slab, up to `depth` K-slabs ahead of the one being converted, so
       // tens of KB per SM are in flight without holding registers.  Each thread then rewrites ITS OWN pieces in place as
@@ -423,10 +548,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t buf_stride = MODE == 3 ? 64u : (uint32_t)(2 * p.Nc);
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (MODE == 3) {            // five stem GEMM tiles (K = 32, N = 32) against the resident stem weight image
+          const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+          const uint32_t bs_hi = smem_u32(halo), bs_lo = bs_hi + 4096;
+          for (int j = 0; j < 5; ++j) {
+            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dm = tmem_base + (uint32_t)acc * buf_stride, dc = dm + 32;
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(a_ring + (size_t)stage * 2 * TC_SLAB_BYTES), a_lo = a_hi + TC_SLAB_BYTES;
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t ko = (uint32_t)k4 * 32u;
+              mma_tf32(dc, make_desc(a_lo + ko), make_desc(bs_hi + ko), idesc_s, k4 > 0);
+              mma_tf32(dc, make_desc(a_hi + ko), make_desc(bs_lo + ko), idesc_s, 1);
+              mma_tf32(dm, make_desc(a_hi + ko), make_desc(bs_hi + ko), idesc_s, k4 > 0);
+            }
+            mma_commit(smem_u32(&empty_bar[stage]));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            mma_commit(smem_u32(&tfull_bar[acc]));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          }
+        }
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * p.Nc);
+        const uint32_t d_main = tmem_base + (uint32_t)acc * buf_stride;
         const uint32_t d_corr = d_main + (uint32_t)p.Nc;
         uint32_t first = 0;
         for (int s = 0; s < p.nslab; ++s) {
@@ -467,13 +615,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
     int acc = 0;
-    uint32_t acc_phase = 0;
+    uint32_t acc_phase = 0, hphase = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
-      const int rows_ok = MODE == 2 ? 32 : min(32, M - mw);   // rows of this warp inside the matrix
+      const int rows_ok = MODE >= 2 ? 32 : min(32, M - mw);   // rows of this warp inside the matrix
       // element offset of the output row for each of the 8 rows this lane owns, -1 = outside
       int orow[8];
-      if (MODE == 2) {
+      if (MODE >= 2) {
         const int per_img = p.tiles_x * p.tiles_y;
         const int b = tile / per_img, rem = tile - b * per_img;
         const int y0 = (rem / p.tiles_x) * TC_TILE_H, x0 = (rem % p.tiles_x) * TC_TILE_W;
@@ -500,9 +648,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
           while (ox >= c.Wout) { ox -= c.Wout; if (++oy == c.Hout) { oy = 0; if (b + 1 < c.B) ++b; } }
         }
       }
+      if (MODE == 3) {
+        // drain the five stem GEMM tiles into the shared-memory halo: bias + ReLU, zero outside the stem output
+        unsigned char* halb = halo + 8192;
+        const int per_img = p.tiles_x * p.tiles_y;
+        const int rem = tile % per_img;
+        const int sy0 = (rem / p.tiles_x) * TC_TILE_H * 2 - 1, sx0 = (rem % p.tiles_x) * TC_TILE_W * 2 - 1;
+        mbar_wait(smem_u32(halo_empty), hphase ^ 1);          // previous tile's slabs have been gathered
+        hphase ^= 1;
+        for (int j = 0; j < 5; ++j) {
+          mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 64u;
+          uint32_t v[32], w[32];
+          tmem_ld32_nowait(ta, v);
+          tmem_ld32_nowait(ta + 32, w);
+          tmem_ld_wait();
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          const int pix = j * 128 + q * 32 + lane;
+          if (pix < S3_HALO_PIX) {
+            const int hy = pix / S3_HALO_W, hx = pix - hy * S3_HALO_W;
+            const int sy = sy0 + hy, sx = sx0 + hx;
+            const bool in_img = sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+              float4 o;
+              o.x = fmaxf(__uint_as_float(v[4 * g4 + 0]) + __uint_as_float(w[4 * g4 + 0]) + __ldg(c.w2 + 864 + 4 * g4 + 0), 0.f);
+              o.y = fmaxf(__uint_as_float(v[4 * g4 + 1]) + __uint_as_float(w[4 * g4 + 1]) + __ldg(c.w2 + 864 + 4 * g4 + 1), 0.f);
+              o.z = fmaxf(__uint_as_float(v[4 * g4 + 2]) + __uint_as_float(w[4 * g4 + 2]) + __ldg(c.w2 + 864 + 4 * g4 + 2), 0.f);
+              o.w = fmaxf(__uint_as_float(v[4 * g4 + 3]) + __uint_as_float(w[4 * g4 + 3]) + __ldg(c.w2 + 864 + 4 * g4 + 3), 0.f);
+              if (!in_img) o = make_float4(0.f, 0.f, 0.f, 0.f);
+              *reinterpret_cast<float4*>(halb + (size_t)pix * 128 + ((g4 ^ (pix & 7)) << 4)) = o;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(halo_full));
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * p.Nc);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (MODE == 3 ? 64u : (uint32_t)(2 * p.Nc));
       for (int col = 0; col < p.Nc; col += 32) {
         const int wcols = min(32, p.Nc - col);                // 32, or 16 for the last block
         {
@@ -645,6 +833,12 @@ bool tc_plan(int K, int N, int anchors, int mode, int* Nc_out, int* nchunks_out,
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
     size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
     int halo_slots = 0;
+    if (mode == 3) {                             // stem-output halo + input patch, 2 A stages
+      fixed += (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES + 2 * 2 * TC_SLAB_BYTES;
+      if (fixed > (size_t)TC_SMEM_BUDGET) continue;
+      *Nc_out = Nc; *nchunks_out = nch; *stages_out = 2; *halo_slots_out = 0;
+      return true;
+    }
     if (mode == 2) {                             // halo ring (2..3 slots) + depthwise weights, 2 A stages
       fixed += (size_t)9 * nslab * 32 * 4 + 2 * 2 * TC_SLAB_BYTES;
       if (fixed + 2 * TC_HALO_BYTES > (size_t)TC_SMEM_BUDGET) continue;
@@ -668,15 +862,20 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.mode = mode;
   static const int raw_hi_env = [] { const char* e = getenv("YL_TC_RAWHI"); return e ? atoi(e) : 1; }();
   p.raw_hi = raw_hi_env;
-  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
+  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;      // mode 3: c.Cin = 32 stem channels, KS = 3 -> 288
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
   YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, &p.Nc, &p.nchunks, &p.stages, &p.halo_slots), "shape does not fit the tcgen05 conv kernel");
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
-  YL_REQUIRE(mode != 3 && (c.Cin & 3) == 0, "tcgen05 conv needs NHWC input with Cin % 4 == 0");
+  YL_REQUIRE((c.Cin & 3) == 0, "tcgen05 conv needs Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
   p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
-  if (mode == 2) {
+  if (mode == 3) {
+    YL_REQUIRE(c.Cin == 32 && c.KS == 3 && c.stride == 2 && c.w2, "fused stem kernel: 3x3 s2 stem with 32 channels -> 3x3 s2 conv");
+    p.Hs = (c.Hin + 2 - 3) / 2 + 1;
+    p.Ws = (c.Win + 2 - 3) / 2 + 1;
+  }
+  if (mode >= 2) {
     YL_REQUIRE(!c.res && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0, "fused DWConvBlock epilogue takes no residual/upsample/head layout");
     p.tiles_x = (c.Wout + TC_TILE_W - 1) / TC_TILE_W;
     p.tiles_y = (c.Hout + TC_TILE_H - 1) / TC_TILE_H;
@@ -687,15 +886,18 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   YL_REQUIRE(!c.up || (long long)c.B * c.Hu * c.Wu * c.Cout < (1ll << 31), "upsample source too large for 32-bit offsets");
   int cols = 32;
   while (cols < 4 * p.Nc) cols <<= 1;
+  if (mode == 3) { YL_REQUIRE(p.Nc <= 32, "fused stem kernel: N chunk <= 32"); cols = 128; }
   p.tmem_cols = cols;
   const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES +
                       (p.dense_epi ? (size_t)4 * 32 * p.Nc * 4 : 0) +
-                      (mode == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES + (size_t)9 * p.nslab * 32 * 4 : 0) + 1024;
+                      (mode == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES + (size_t)9 * p.nslab * 32 * 4 : 0) +
+                      (mode == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0) + 1024;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int gx = sm_count / p.nchunks;
@@ -704,7 +906,8 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   dim3 grid(gx, p.nchunks);
   if (mode == 0) tc_conv_kernel<0><<<grid, TC_THREADS, smem, st>>>(p);
   else if (mode == 1) tc_conv_kernel<1><<<grid, TC_THREADS, smem, st>>>(p);
-  else tc_conv_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
+  else if (mode == 2) tc_conv_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
+  else tc_conv_kernel<3><<<grid, TC_THREADS, smem, st>>>(p);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -22,7 +22,7 @@ def _stream_ptr(device) -> ctypes.c_void_p:
 
 class YoloLiteB200:
     def __init__(self, state_dict: dict, meta: dict, device="cuda:0", fuse_dwpw: bool = True,
-                 reuse_buffers: bool = True, tensor_cores: bool = True):
+                 reuse_buffers: bool = True, tensor_cores: bool = True, fuse_stem: bool = True):
         lib = L.lib()                                   # raises ImportError if the extension is not built
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -31,7 +31,7 @@ class YoloLiteB200:
             raise RuntimeError("no CUDA device visible: yololite_b200 has no CPU fallback")
         self.meta = meta
         self.program = packer.lower(state_dict, meta, fuse_dwpw=fuse_dwpw, reuse_buffers=reuse_buffers,
-                                    tensor_cores=tensor_cores)
+                                    tensor_cores=tensor_cores, fuse_stem=fuse_stem)
         cfg = self.program.cfg
         self.cfg = cfg
         self.num_classes = cfg.num_classes

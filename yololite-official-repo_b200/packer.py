@@ -185,7 +185,7 @@ def _pad4(b: np.ndarray) -> np.ndarray:
 
 
 def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True,
-          tensor_cores: bool = True) -> Program:
+          tensor_cores: bool = True, fuse_stem: bool = True) -> Program:
     cfg = parse_meta(meta)
     sd = _SD(state_dict)
     P = Program(cfg=cfg)
@@ -199,7 +199,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
                           w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
                           w2_off=(-1 if w2 is None else P.add_blob(w2)),
                           wt_off=(P.add_blob(tc_image(np.asarray(w, np.float64).reshape(-1, w.shape[-1]), cout))
-                                  if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW) and cout >= 8 and w.shape[0] >= 8 else -1)))
+                                  if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW, L.OP_STEM2) and cout >= 8 and w.shape[0] >= 8 else -1)))
         return dst
 
     def conv_bn(x: Optional[_T], wkey, bnkey, k, stride, act, red, res=None) -> _T:
@@ -221,13 +221,31 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     # ---------------- backbone
     table, mult, stem_c = BACKBONES[cfg.backbone]
     bb = "backbone."
-    x = conv_bn(None, bb + "conv_stem", bb + "bn1", 3, 2, L.ACT_RELU, 2)
-    feats = [x]
-    red = 2
+    first = table[0][0]
+    # the stem feature itself is never tapped (the FPN takes the last 3-4 taps), so conv_stem can be fused with
+    # blocks.0.0 when both are 3x3 s2 and the stem has 32 channels
+    fused_stem = bool(fuse_stem and tensor_cores and stem_c == 32 and first[0] == "cn" and first[1] == 3 and first[2] == 2)
+    if fused_stem:
+        ws = sd.get(bb + "conv_stem.weight")
+        s0, b0 = sd.bn(bb + "bn1")
+        ws = np.transpose(ws * s0[:, None, None, None], (2, 3, 1, 0)).reshape(27, stem_c)
+        key = bb + "blocks.0.0"
+        w1 = sd.get(key + ".conv.weight")
+        s1, b1 = sd.bn(key + ".bn1")
+        x = emit(L.OP_STEM2, None, int(w1.shape[0]), 4, k=3, stride=2, act=L.ACT_RELU, w=_gemm_w(w1 * s1[:, None, None, None]),
+                 b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(ws, stem_c).astype(np.float64)]), k2=stem_c)
+        feats = [_T(-1, stem_c, 2)]
+        red = 4
+    else:
+        x = conv_bn(None, bb + "conv_stem", bb + "bn1", 3, 2, L.ACT_RELU, 2)
+        feats = [x]
+        red = 2
     for si, stage in enumerate(table):
         for bi, spec in enumerate(stage):
             key = f"{bb}blocks.{si}.{bi}"
-            if spec[0] == "cn":
+            if fused_stem and si == 0 and bi == 0:
+                pass
+            elif spec[0] == "cn":
                 _, k, s, c = spec
                 red *= s
                 x = conv_bn(x, key + ".conv", key + ".bn1", k, s, L.ACT_RELU, red)
