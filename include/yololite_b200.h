@@ -136,6 +136,10 @@ int yl_decode(const float* const* level_logits, const int32_t* level_dims, int32
 int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t pitch, float* dst, int32_t S,
                   int32_t nh, int32_t nw, int32_t left, int32_t top, void* stream);
 
+/* Same for a contiguous batch of B equally sized images: src [B,h0,w0,3] uint8 (device), dst [B,3,S,S] fp32.  */
+int yl_preprocess_batch(const uint8_t* src, int32_t B, int32_t h0, int32_t w0, float* dst, int32_t S, int32_t nh, int32_t nw,
+                        int32_t left, int32_t top, void* stream);
+
 /* Process-wide launch counters: key "tc_launches" (tcgen05 conv kernel), "simt_launches" (fp32 SIMT conv kernels),
  * "post_launches".  Unknown key -> -1.  Lets tests assert WHICH kernel a call used.                       */
 long long yl_stat(const char* key);

@@ -47,7 +47,8 @@ def build(kind, cin, cout, k, stride, act, up, res):
         op.w_off = add(wm)
         op.wt_off = add(packer.tc_image(wm, cout))
         wsm = g.randn(27, 32) / 5
-        op.w2_off = add(np.concatenate([wsm.reshape(-1), g.randn(32) * 0.3, packer.tc_image(wsm, 32).astype(np.float64)]))
+        bsv = g.randn(32) * 0.3
+        op.w2_off = add(np.concatenate([wsm.reshape(-1), bsv, packer.tc_image(np.concatenate([wsm, bsv.reshape(1, -1)]), 32).astype(np.float64)]))
     else:
         kk = 1 if kind == "dwpw" else k
         wm = np.zeros((kk * kk * cin, (cout + 3) // 4 * 4))

@@ -212,7 +212,7 @@ def test_fused_stem_conv(hw, n2):
     op.w_off = add(wm)
     op.wt_off = add(packer.tc_image(wm, n2))
     wsm = np.transpose(ws.double().numpy(), (2, 3, 1, 0)).reshape(27, 32)
-    op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(wsm, 32).astype(np.float64)]))
+    op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(np.concatenate([wsm, bs.double().numpy().reshape(1, -1)]), 32).astype(np.float64)]))
     op.b_off = add(packer._pad4(b2.double().numpy()))
     dblob = torch.from_numpy(np.concatenate(blob)).cuda()
     want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()

@@ -7,6 +7,7 @@ from ._lib import EXPORTS, LIB_PATH, lib            # noqa: F401
 from .engine import YoloLiteB200                    # noqa: F401
 from .post import (Detections, PostProcessor, backmap, decode_batch_to_coco_dets,   # noqa: F401
                    decode_preds_anchorfree, detect)
-from .infer import YoloLite, letterbox_geometry, load_model_names_imgsize_from_ckpt, preprocess  # noqa: F401
+from .infer import (YoloLite, letterbox_geometry, load_model_names_imgsize_from_ckpt, preprocess,   # noqa: F401
+                    preprocess_batch)
 
 __version__ = "0.1.0"

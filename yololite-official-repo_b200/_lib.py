@@ -42,6 +42,8 @@ _SIGNATURES = {
                                  ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "yl_preprocess": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32,
                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
+    "yl_preprocess_batch": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
     "yl_stat": (ctypes.c_longlong, [ctypes.c_char_p]),
     "yl_last_error": (ctypes.c_char_p, []),
     "yl_abi_version": (ctypes.c_int, []),

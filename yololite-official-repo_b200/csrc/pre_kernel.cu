@@ -13,6 +13,7 @@ struct PreParams {
   const unsigned char* src;
   float* dst;
   int h0, w0, pitch, S, nh, nw, left, top;
+  size_t src_stride, dst_stride;   // per image (batched launch: blockIdx.z)
 };
 
 __device__ __forceinline__ void lin_coef(int d, int n_src, double scale, bool clamp, int& i0, int& i1, int& a0, int& a1) {
@@ -33,6 +34,8 @@ __global__ void __launch_bounds__(256) pre_kernel(PreParams p) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= p.S) return;
+  p.src += (size_t)blockIdx.z * p.src_stride;
+  p.dst += (size_t)blockIdx.z * p.dst_stride;
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
   int bgr[3] = {114, 114, 114};
@@ -74,8 +77,21 @@ extern "C" int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t
   YL_REQUIRE(src && dst, "null pointer");
   YL_REQUIRE(h0 >= 1 && w0 >= 1 && pitch >= w0 * 3 && S >= 1, "bad image geometry");
   YL_REQUIRE(nh >= 1 && nw >= 1 && left >= 0 && top >= 0 && left + nw <= S && top + nh <= S, "letterbox does not fit");
-  PreParams p{src, dst, h0, w0, pitch, S, nh, nw, left, top};
+  PreParams p{src, dst, h0, w0, pitch, S, nh, nw, left, top, 0, 0};
   dim3 grid((S + 255) / 256, S);
+  pre_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  YL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int yl_preprocess_batch(const uint8_t* src, int32_t B, int32_t h0, int32_t w0, float* dst, int32_t S, int32_t nh,
+                                   int32_t nw, int32_t left, int32_t top, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(src && dst && B >= 1, "null pointer / empty batch");
+  YL_REQUIRE(h0 >= 1 && w0 >= 1 && S >= 1, "bad image geometry");
+  YL_REQUIRE(nh >= 1 && nw >= 1 && left >= 0 && top >= 0 && left + nw <= S && top + nh <= S, "letterbox does not fit");
+  PreParams p{src, dst, h0, w0, w0 * 3, S, nh, nw, left, top, (size_t)h0 * w0 * 3, (size_t)3 * S * S};
+  dim3 grid((S + 255) / 256, S, B);
   pre_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;

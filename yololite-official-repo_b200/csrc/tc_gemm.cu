@@ -72,12 +72,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   for (uint32_t spin = 0; !ok; ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(2000u)      // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
-    if (spin > (1u << 24)) asm volatile("trap;");   // protocol error: fail loudly, never hang the device
+    if (spin > (1u << 22)) asm volatile("trap;");   // protocol error: fail loudly, never hang the device
   }
 }
 
@@ -268,6 +268,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
         const int k = ch * 4 + q, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
         poff[q] = k < 27 ? (ci * S3_PATCH_H + ky) * S3_PATCH_PITCH + kx : -1;
       }
+      uint32_t soff[4];
+      int hp0[4];                                     // halo pixel of tap (0,0) for this thread's 4 output rows
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = r0 + 32 * i;
+        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+        hp0[i] = 2 * (row >> 4) * S3_HALO_W + 2 * (row & 15);
+      }
       auto issue_patch = [&](int tile) {
         if (tile < tiles) {
           const int b = tile / per_img, rem = tile - b * per_img;
@@ -298,34 +306,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");              // patch landed for everyone
-        // ---- stem A tiles: 5 x 128 halo pixels, one K-slab each
-        for (int j = 0; j < 5; ++j) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+        // ---- stem A tiles: 5 x 128 halo pixels, one K-slab each (k = 27 is the constant 1 that multiplies the bias row)
+        {
+          int hy = r0 / S3_HALO_W, hx = r0 - hy * S3_HALO_W;         // pixel r0 of the halo, then steps of 32 pixels
+          for (int j = 0; j < 5; ++j) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int row = r0 + 32 * i, pix = j * 128 + row;
-            float e[4] = {0.f, 0.f, 0.f, 0.f};
-            if (pix < S3_HALO_PIX) {
-              const int hy = pix / S3_HALO_W, hx = pix - hy * S3_HALO_W;
+            for (int i = 0; i < 4; ++i) {
+              const bool ok = hy < S3_HALO_H;
               const float* pb = patch + 2 * hy * S3_PATCH_PITCH + 2 * hx;
+              float e[4];
 #pragma unroll
-              for (int q = 0; q < 4; ++q)
-                if (poff[q] >= 0) e[q] = pb[poff[q]];
+              for (int q = 0; q < 4; ++q) e[q] = (ok && poff[q] >= 0) ? pb[poff[q]] : 0.f;
+              if (ch == 6) e[3] = ok ? 1.f : 0.f;
+              float4 l;
+              l.x = e[0] - __uint_as_float(__float_as_uint(e[0]) & 0xFFFFE000u);
+              l.y = e[1] - __uint_as_float(__float_as_uint(e[1]) & 0xFFFFE000u);
+              l.z = e[2] - __uint_as_float(__float_as_uint(e[2]) & 0xFFFFE000u);
+              l.w = e[3] - __uint_as_float(__float_as_uint(e[3]) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(hi + soff[i]) = make_float4(e[0], e[1], e[2], e[3]);
+              *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+              hx += 32;
+              if (hx >= S3_HALO_W) { hx -= S3_HALO_W; ++hy; }
             }
-            const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-            float4 l;
-            l.x = e[0] - __uint_as_float(__float_as_uint(e[0]) & 0xFFFFE000u);
-            l.y = e[1] - __uint_as_float(__float_as_uint(e[1]) & 0xFFFFE000u);
-            l.z = e[2] - __uint_as_float(__float_as_uint(e[2]) & 0xFFFFE000u);
-            l.w = e[3] - __uint_as_float(__float_as_uint(e[3]) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(hi + off) = make_float4(e[0], e[1], e[2], e[3]);
-            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + off) = l;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");              // everyone is done reading the patch
         issue_patch(tile + gridDim.x);
@@ -333,22 +342,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
         hphase ^= 1;
         // ---- the 9 taps = 9 K-slabs gathered from the halo (chunk c of pixel q sits at position c ^ (q & 7))
         for (int s = 0; s < 9; ++s) {
-          const int ky = s / 3, kx = s - ky * 3;
+          const int tapoff = (s / 3) * S3_HALO_W + (s % 3);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = r0 + 32 * i, ty = row >> 4, tx = row & 15;
-            const int hp = (2 * ty + ky) * S3_HALO_W + 2 * tx + kx;
-            const float4 a = *reinterpret_cast<const float4*>(halb + (size_t)hp * 128 + ((ch ^ (hp & 7)) << 4));
-            const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+            const int hp = hp0[i] + tapoff;
+            const float4 a = *reinterpret_cast<const float4*>(halb + hp * 128 + ((ch ^ (hp & 7)) << 4));
             float4 l;
             l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
             l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
             l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
             l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(hi + off) = a;                 // the tensor core drops the low 13 bits itself
-            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + off) = l;
+            *reinterpret_cast<float4*>(hi + soff[i]) = a;              // the tensor core drops the low 13 bits itself
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
@@ -676,10 +683,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 #pragma unroll
             for (int g4 = 0; g4 < 8; ++g4) {
               float4 o;
-              o.x = fmaxf(__uint_as_float(v[4 * g4 + 0]) + __uint_as_float(w[4 * g4 + 0]) + __ldg(c.w2 + 864 + 4 * g4 + 0), 0.f);
-              o.y = fmaxf(__uint_as_float(v[4 * g4 + 1]) + __uint_as_float(w[4 * g4 + 1]) + __ldg(c.w2 + 864 + 4 * g4 + 1), 0.f);
-              o.z = fmaxf(__uint_as_float(v[4 * g4 + 2]) + __uint_as_float(w[4 * g4 + 2]) + __ldg(c.w2 + 864 + 4 * g4 + 2), 0.f);
-              o.w = fmaxf(__uint_as_float(v[4 * g4 + 3]) + __uint_as_float(w[4 * g4 + 3]) + __ldg(c.w2 + 864 + 4 * g4 + 3), 0.f);
+              o.x = fmaxf(__uint_as_float(v[4 * g4 + 0]) + __uint_as_float(w[4 * g4 + 0]), 0.f);      // bias rides in the GEMM (k = 27)
+              o.y = fmaxf(__uint_as_float(v[4 * g4 + 1]) + __uint_as_float(w[4 * g4 + 1]), 0.f);
+              o.z = fmaxf(__uint_as_float(v[4 * g4 + 2]) + __uint_as_float(w[4 * g4 + 2]), 0.f);
+              o.w = fmaxf(__uint_as_float(v[4 * g4 + 3]) + __uint_as_float(w[4 * g4 + 3]), 0.f);
               if (!in_img) o = make_float4(0.f, 0.f, 0.f, 0.f);
               *reinterpret_cast<float4*>(halb + (size_t)pix * 128 + ((g4 ^ (pix & 7)) << 4)) = o;
             }

@@ -64,6 +64,22 @@ def preprocess(images_bgr: Sequence[Union[np.ndarray, torch.Tensor]], img_size: 
     return x, geo
 
 
+def preprocess_batch(images_u8: torch.Tensor, img_size: int, out: Optional[torch.Tensor] = None, letterbox: bool = True):
+    """A CUDA uint8 [B,H,W,3] BGR batch (equal sizes) -> normalised fp32 [B,3,S,S] in ONE launch + the shared geometry."""
+    if not (images_u8.is_cuda and images_u8.dtype == torch.uint8 and images_u8.dim() == 4 and images_u8.shape[3] == 3):
+        raise ValueError("expected a CUDA uint8 tensor [B,H,W,3]")
+    images_u8 = images_u8.contiguous()
+    B, h0, w0, _ = images_u8.shape
+    if letterbox:
+        scale, nh, nw, left, top = letterbox_geometry(h0, w0, img_size)
+    else:
+        scale, nh, nw, left, top = min(img_size / h0, img_size / w0), img_size, img_size, 0, 0
+    x = out if out is not None else torch.empty((B, 3, img_size, img_size), device=images_u8.device, dtype=torch.float32)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(images_u8.device).cuda_stream)
+    L.check(L.lib().yl_preprocess_batch(images_u8.data_ptr(), B, h0, w0, x.data_ptr(), img_size, nh, nw, left, top, stream))
+    return x, (scale, left, top, h0, w0)
+
+
 class YoloLite:
     """`YoloLite(weights).predict(source)` -> list of result dicts (README.md:22-42)."""
 
@@ -112,6 +128,18 @@ class YoloLite:
         for r in results:
             r["speed"] = dict(speed)
         return results
+
+    def predict_batch(self, images_u8: torch.Tensor, conf: float = 0.4, iou: float = 0.5, max_det: int = 300, img_size: int = 0,
+                      cap: Optional[int] = None):
+        """Batched device-side predict: uint8 [B,H,W,3] BGR (CUDA) -> Detections (fixed capacity, letterboxed coordinates)
+        + the letterbox geometry.  No host synchronisation; call `.to_list()` / `backmap` on the result when needed."""
+        S = int(img_size) if img_size else self.img_size
+        key = (tuple(images_u8.shape), S)
+        if getattr(self, "_xbuf_key", None) != key:
+            self._xbuf = torch.empty((images_u8.shape[0], 3, S, S), device=images_u8.device, dtype=torch.float32)
+            self._xbuf_key = key
+        x, geo = preprocess_batch(images_u8, S, out=self._xbuf)
+        return self._post(self.model(x), S, conf, iou, max_det, cap), geo
 
     def to_json(self, result: dict) -> dict:
         """The per-image JSON record tools/infer.py:540-549 writes."""

@@ -233,7 +233,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         w1 = sd.get(key + ".conv.weight")
         s1, b1 = sd.bn(key + ".bn1")
         x = emit(L.OP_STEM2, None, int(w1.shape[0]), 4, k=3, stride=2, act=L.ACT_RELU, w=_gemm_w(w1 * s1[:, None, None, None]),
-                 b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(ws, stem_c).astype(np.float64)]), k2=stem_c)
+                 b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
         feats = [_T(-1, stem_c, 2)]
         red = 4
     else:
