@@ -195,7 +195,7 @@ def calibrate_obj_bias(y, ckpt_fn, x, a):
 
 def run_b200(a):
     import yololite_b200 as y
-    from yololite_b200 import synth
+    from yololite_b200 import dist as ydist, synth
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -231,11 +231,8 @@ def run_b200(a):
         eng.forward(xin, out=outs)
         d = post(outs, S, a.conf, a.iou, a.max_det, cap=a.cap)
         if world > 1:      # the path's one exchange: gather the fixed-capacity detections
-            packed[..., :4] = d.boxes
-            packed[..., 4] = d.scores
-            packed[..., 5] = d.classes.float()
-            dist.all_gather_into_tensor(gathered, packed)
-            dist.all_gather_into_tensor(gcounts, d.counts)
+            ydist.pack_detections(d.boxes, d.scores, d.classes, out=packed)
+            ydist.gather_detections(packed, d.counts, out=gathered, out_counts=gcounts)
         return d
 
     def sync_all():
