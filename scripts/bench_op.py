@@ -34,7 +34,7 @@ def build(kind, cin, cout, k, stride, act, up, res):
     op = L.YlOp()
     op.kind, op.k, op.stride, op.act, op.anchors = KINDS[kind], k, stride, act, 0
     op.src, op.dst, op.res, op.up = 0, 1, (2 if res else -1), (3 if up else -1)
-    op.k2, op.w2_off, op.wt_off = 0, -1, -1
+    op.k2, op.w2_off, op.wt_off, op.w3_off = 0, -1, -1, -1
     op.cin, op.cout = cin, cout
     if kind == "dw":
         op.w_off = add(g.randn(k * k, cin) / k)
@@ -48,6 +48,7 @@ def build(kind, cin, cout, k, stride, act, up, res):
         op.wt_off = add(packer.tc_image(wm, cout))
         wsm = g.randn(27, 32) / 5
         bsv = g.randn(32) * 0.3
+        op.w3_off = add(packer.stem2_image(wm, cout, wsm, bsv))
         op.w2_off = add(np.concatenate([wsm.reshape(-1), bsv, packer.tc_image(np.concatenate([wsm, bsv.reshape(1, -1)]), 32).astype(np.float64)]))
     else:
         kk = 1 if kind == "dwpw" else k

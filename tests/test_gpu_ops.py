@@ -32,7 +32,7 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
     op = L.YlOp()
     op.kind, op.k, op.stride, op.act, op.anchors = kind, k, stride, act, anchors
     op.src, op.dst, op.res, op.up = 0, 1, (2 if res is not None else -1), (3 if up is not None else -1)
-    op.k2, op.w2_off, op.wt_off = 0, -1, -1
+    op.k2, op.w2_off, op.wt_off, op.w3_off = 0, -1, -1, -1
     if kind == L.OP_DW:
         op.cin = op.cout = cout
         op.w_off = add(np.transpose(wn, (2, 3, 1, 0)).reshape(k * k, cout))
@@ -182,9 +182,11 @@ def test_tensor_core_path_is_not_single_pass_tf32():
     assert L.lib().yl_stat(b"simt_launches") == n1 + 1
 
 
-@pytest.mark.parametrize("hw,n2", [((64, 64), 16), ((45, 52), 16), ((83, 38), 32), ((640, 640), 16)])
-def test_fused_stem_conv(hw, n2):
-    """YL_OP_STEM2: conv_stem (3x3 s2, 3->32, ReLU) -> 3x3 s2 conv (32->n2, ReLU) in one tcgen05 kernel."""
+@pytest.mark.parametrize("bf16x3", [True, False])
+@pytest.mark.parametrize("hw,n2", [((64, 64), 16), ((45, 52), 16), ((83, 38), 32), ((640, 640), 16), ((96, 100), 12), ((33, 36), 16)])
+def test_fused_stem_conv(hw, n2, bf16x3):
+    """YL_OP_STEM2: conv_stem (3x3 s2, 3->32, ReLU) -> 3x3 s2 conv (32->n2, ReLU) in one tcgen05 kernel.
+    bf16x3 = the bf16-triple kernel (csrc/stem_kernel.cu, w3_off image); otherwise the older 3xTF32 kernel (w3_off = -1)."""
     from yololite_b200 import _lib as L, packer
     g = torch.Generator().manual_seed(hw[0] + n2)
     B = 2 if hw[0] < 600 else 1
@@ -213,6 +215,7 @@ def test_fused_stem_conv(hw, n2):
     op.wt_off = add(packer.tc_image(wm, n2))
     wsm = np.transpose(ws.double().numpy(), (2, 3, 1, 0)).reshape(27, 32)
     op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(np.concatenate([wsm, bs.double().numpy().reshape(1, -1)]), 32).astype(np.float64)]))
+    op.w3_off = add(packer.stem2_image(wm, n2, wsm, bs.double().numpy())) if bf16x3 else -1
     op.b_off = add(packer._pad4(b2.double().numpy()))
     dblob = torch.from_numpy(np.concatenate(blob)).cuda()
     want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()

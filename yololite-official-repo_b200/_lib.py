@@ -12,7 +12,7 @@ class YlOp(ctypes.Structure):
                 ("up", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("act", ctypes.c_int32), ("anchors", ctypes.c_int32),
                 ("k2", ctypes.c_int32), ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
-                ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64)]
+                ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64), ("w3_off", ctypes.c_int64)]
 
 
 OP_STEM, OP_CONV, OP_DW, OP_DWPW, OP_STEM2 = 0, 1, 2, 3, 4

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libyololite_b200.so")
-SOURCES = ["engine.cu", "conv_kernels.cu", "tc_gemm.cu", "post_kernel.cu", "pre_kernel.cu"]
+SOURCES = ["engine.cu", "conv_kernels.cu", "tc_gemm.cu", "stem_kernel.cu", "post_kernel.cu", "pre_kernel.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

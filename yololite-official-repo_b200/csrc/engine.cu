@@ -1,5 +1,6 @@
 // C ABI + layer-program executor (see include/yololite_b200.h).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -40,6 +41,8 @@ namespace yl {
 
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
 bool tc_plan(int K, int N, int anchors, int mode, int* Nc, int* nchunks, int* stages, int* halo_slots);
+bool stem2_supported(const ConvParams& c);
+int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st);
 
 static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
                   int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st) {
@@ -59,6 +62,8 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   if (op.kind == YL_OP_STEM2) {
     p.Cin = op.k2;                                // K of the second conv = 9 * stem channels
     ++g_tc_launches;
+    static const int old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
+    if (op.w3_off >= 0 && !old_stem && stem2_supported(p)) return launch_stem2(p, blob + op.w3_off, sm_count, st);
     return launch_tc_conv(p, blob + op.wt_off, 3, sm_count, st);
   }
   if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {

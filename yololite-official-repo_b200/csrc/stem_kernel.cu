@@ -1,0 +1,449 @@
+// Fused conv_stem (3x3 s2, Cin = 3, 32 ch, BN + ReLU) -> blocks.0.0 (3x3 s2 dense conv, BN + ReLU) on tcgen05, sm_100a.
+// Reference: timm mobilenetv4_conv_small[_050] as called at scripts/model/model_v2.py:266-272; layer shapes from
+// YoloLite_custom_training.ipynb:392-410.  The 13 MB/image stem activation never reaches HBM.
+//
+// Operands are error-compensated bf16 triples: every fp32 value x = x1 + x2 + x3 (x1 = bf16(x), x2 = bf16(x - x1),
+// x3 = bf16(x - x1 - x2)), D = A1*W1 (main accumulator) + A1*W2 + A2*W1 + A2*W2 + A1*W3 + A3*W1 (correction accumulator),
+// dropped terms are 2^-24 relative.  uint8 images are exact in ONE bf16, so the image path runs 3 passes instead of 6.
+//
+// Per 16x8 tile of conv2 output pixels (one persistent CTA per SM, 17 warps, warp-specialised):
+//   warps 8-15  producers: cp.async the 3 x 67 x 36 fp32 input patch (NCHW) into shared memory, build the stem's im2col
+//               operand (K = 27 taps + a constant-1 column that carries the folded BN bias, padded to 32) for five
+//               128-row tiles covering the 33 x 17 halo of stem output pixels;
+//   warp  16    one thread issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128, N = 32, K = 32) into five TMEM
+//               accumulator pairs, GEMM2 = conv2 as nine per-tap GEMMs (M = 128, N = 16, K = 32);
+//   warps 0-7   epilogue: TMEM -> ReLU -> bf16 triple -> shared-memory halo stored as four parity planes
+//               (row parity x column parity); then conv2's accumulator -> bias + ReLU -> NHWC global stores.
+// GEMM2 has NO im2col copy: for tap (ky, kx) the A operand of the 16x8 tile is the parity plane (ky&1, kx&1) shifted
+// by (ky>>1, kx>>1) pixels, which a K-major SWIZZLE_64B descriptor addresses directly (8-row atoms = 8 consecutive
+// output columns, stride-byte-offset = plane pitch).  The hardware swizzle is a function of the shared-memory ADDRESS
+// (verified on B200, experiments/exp_desc.cu), so start addresses / SBOs that are not multiples of the 512 B atom work
+// as long as the data was written with the same address-based XOR.
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace yl {
+
+constexpr int S2_EPI_WARPS = 8, S2_PROD_WARPS = 8, S2_MMA_WARP = 16, S2_THREADS = 17 * 32;
+constexpr int S2_TH = 16, S2_TW = 8;                       // conv2 output tile (rows x cols) = 128 pixels
+constexpr int S2_HH = 2 * S2_TH + 1, S2_HW = 2 * S2_TW + 1; // stem-output halo 33 x 17
+constexpr int S2_HPIX = S2_HH * S2_HW;                     // 561
+constexpr int S2_MT = (S2_HPIX + 127) / 128;               // 5 stem GEMM tiles
+constexpr int S2_PR = 2 * S2_HH + 1;                       // 67 patch rows
+constexpr int S2_PP = 36;                                  // patch pitch (floats): 16 B-aligned superset of the 35 columns
+constexpr int S2_PLANE_BYTES = (S2_HPIX * 64 + 511) / 512 * 512;   // one bf16 split of the halo (32 ch x 2 B per pixel); a multiple of
+                                                                   // the 512 B swizzle period so all three splits share one XOR pattern
+constexpr int S2_A1_SPLIT = 128 * 64, S2_A1_STAGE = 3 * S2_A1_SPLIT;
+constexpr int S2_PATCH_BYTES = 3 * S2_PR * S2_PP * 4;      // 28944
+constexpr int S2_WST_BYTES = 3 * 32 * 64;                  // stem weights, three splits
+// parity planes (py, px): pixel offsets inside one split, pitch 9 (px = 0) or 8 (px = 1)
+__host__ __device__ constexpr int s2_plane_off(int py, int px) { return py ? (px ? 433 : 289) : (px ? 153 : 0); }
+
+struct Stem2Params {
+  const float* __restrict__ in;        // [B,3,H,W] fp32 NCHW
+  const float* __restrict__ wimg;      // bf16 image: [3 splits][9 taps][N2][32] SW64 | [3 splits][32][32] SW64
+  const float* __restrict__ bias2;     // [Cout]
+  float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
+  int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
+  int tiles_x, tiles_y, num_tiles;
+  int pass_mask;                       // debug: bit ps enables pass ps of both GEMMs (default 63)
+};
+
+namespace s2 {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u)
+        : "memory");
+    if (spin > (1u << 22)) asm volatile("trap;");   // protocol error: fail loudly, never hang the device
+  }
+}
+// K-major SWIZZLE_64B descriptor: 8-row groups `sbo` bytes apart
+__device__ __forceinline__ uint64_t desc64(uint32_t saddr, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// two fp32 -> packed bf16 pair (element 0 in the low half) for each of the three splits
+__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  p1 = *reinterpret_cast<uint32_t*>(&h);
+  a -= __uint_as_float(p1 << 16);
+  b -= __uint_as_float(p1 & 0xFFFF0000u);
+  h = __floats2bfloat162_rn(a, b);
+  p2 = *reinterpret_cast<uint32_t*>(&h);
+  a -= __uint_as_float(p2 << 16);
+  b -= __uint_as_float(p2 & 0xFFFF0000u);
+  h = __floats2bfloat162_rn(a, b);
+  p3 = *reinterpret_cast<uint32_t*>(&h);
+}
+}  // namespace s2
+
+__global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
+  using namespace s2;
+  extern __shared__ unsigned char smem_unaligned[];
+  unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- shared memory carve-up
+  const int w2_bytes = 27 * p.N2 * 64;                              // conv2 weights: 3 splits x 9 taps x N2 rows x 64 B
+  unsigned char* w2s = smem;                                        // 1024-aligned (N2 % 16 == 0 -> 27 * N2 * 64 % 1024 == 0)
+  unsigned char* wst = w2s + w2_bytes;                              // 6 KB
+  unsigned char* a1 = wst + S2_WST_BYTES;                           // 2 stages x 3 splits x 8 KB (1024-aligned)
+  unsigned char* planes = a1 + 2 * S2_A1_STAGE;                     // 3 splits x 35904 B
+  float* patch = reinterpret_cast<float*>(planes + 3 * S2_PLANE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + S2_PATCH_BYTES);
+  uint64_t* a1_full = bars;            // [2]  producers (8 warps) -> MMA
+  uint64_t* a1_empty = bars + 2;       // [2]  MMA commit -> producers
+  uint64_t* acc1_full = bars + 4;      // [5]  MMA commit -> epilogue
+  uint64_t* acc1_free = bars + 9;      // [5]  epilogue (8 warps) -> MMA
+  uint64_t* halo_full = bars + 14;     //      epilogue (8 warps) -> MMA
+  uint64_t* halo_free = bars + 15;     //      MMA commit -> epilogue
+  uint64_t* acc2_full = bars + 16;     // [2]  MMA commit -> epilogue
+  uint64_t* acc2_free = bars + 18;     // [2]  epilogue (8 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS); mbar_init(smem_u32(&a1_empty[s]), 1); }
+    for (int j = 0; j < S2_MT; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
+    mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
+    mbar_init(smem_u32(halo_free), 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc2_full[b]), 1); mbar_init(smem_u32(&acc2_free[b]), S2_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == S2_MMA_WARP) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  {   // resident weight images, copied verbatim (pre-split, pre-swizzled on the host)
+    const int total4 = (w2_bytes + S2_WST_BYTES) >> 4;
+    for (int i = threadIdx.x; i < total4; i += S2_THREADS)
+      reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(p.wimg) + i);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles = p.num_tiles;
+  const int per_img = p.tiles_x * p.tiles_y;
+  // TMEM columns: stem tile j: main 64j, corr 64j + 32; conv2 buffer b: main 320 + 64b, corr 352 + 64b
+  constexpr uint32_t ACC2_COL = 64 * S2_MT;
+
+  if (warp >= S2_EPI_WARPS && warp < S2_EPI_WARPS + S2_PROD_WARPS) {
+    // =============================== producers ===============================
+    const int t = threadIdx.x - 32 * S2_EPI_WARPS;          // 0..255
+    const int ch = t & 3, r0 = t >> 2;                      // 16 B chunk (8 k's) of rows r0 and r0 + 64
+    int poff[8];                                            // patch offsets of this thread's 8 k's; -1: constant 1, -2: zero
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = ch * 8 + m, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+      poff[m] = k < 27 ? (ci * S2_PR + ky) * S2_PP + kx + 1 : (k == 27 ? -1 : -2);
+    }
+    const size_t plane = (size_t)p.H * p.W;
+    auto issue_patch = [&](int tile) {
+      if (tile < tiles) {
+        const int b = tile / per_img, rem = tile - b * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int iy0 = 4 * S2_TH * ty - 3, ixa = 4 * S2_TW * tx - 4;
+        const float* img = p.in + (size_t)b * 3 * plane;
+        const uint32_t pbase = smem_u32(patch);
+        for (int idx = t; idx < 3 * S2_PR * 9; idx += 32 * S2_PROD_WARPS) {
+          const int row = idx / 9, c4 = idx - row * 9;
+          const int ci = row / S2_PR, iy = iy0 + row - ci * S2_PR, ix = ixa + 4 * c4;
+          const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix + 3 < p.W;
+          const float* src = ok ? img + ci * plane + (size_t)iy * p.W + ix : p.in;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pbase + (uint32_t)(row * S2_PP + 4 * c4) * 4u), "l"(src),
+                       "r"(ok ? 16u : 0u) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_patch(blockIdx.x);
+    uint32_t n = 0;                                          // running stem-tile counter -> A1 stage / phase
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // patch landed for every producer
+      for (int j = 0; j < S2_MT; ++j, ++n) {
+        const uint32_t stage = n & 1u;
+        mbar_wait(smem_u32(&a1_empty[stage]), ((n >> 1) & 1u) ^ 1u);
+        unsigned char* st = a1 + stage * S2_A1_STAGE;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int r = r0 + 64 * i, q = j * 128 + r;
+          if (q < S2_HPIX) {
+            const int hy = q / S2_HW, hx = q - hy * S2_HW;
+            const float* pb = patch + 2 * hy * S2_PP + 2 * hx;
+            float e[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) e[m] = poff[m] >= 0 ? pb[poff[m]] : (poff[m] == -1 ? 1.f : 0.f);
+            uint4 o1, o2, o3;
+            split3(e[0], e[1], o1.x, o2.x, o3.x);
+            split3(e[2], e[3], o1.y, o2.y, o3.y);
+            split3(e[4], e[5], o1.z, o2.z, o3.z);
+            split3(e[6], e[7], o1.w, o2.w, o3.w);
+            const uint32_t off = (uint32_t)r * 64u + (uint32_t)((ch ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4*>(st + off) = o1;
+            *reinterpret_cast<uint4*>(st + S2_A1_SPLIT + off) = o2;
+            *reinterpret_cast<uint4*>(st + 2 * S2_A1_SPLIT + off) = o3;
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&a1_full[stage]));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");         // every producer is done reading the patch
+      issue_patch(tile + gridDim.x);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  } else if (warp == S2_MMA_WARP) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N2 >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t a1_u = smem_u32(a1), wst_u = smem_u32(wst), w2_u = smem_u32(w2s), pl_u = smem_u32(planes);
+      const uint32_t w2_split = 9u * (uint32_t)p.N2 * 64u, w2_tap = (uint32_t)p.N2 * 64u;
+      uint32_t n = 0;
+      // (A split, W split) of the six passes; pass 0 goes to the main accumulator, the rest to the correction accumulator
+      auto gemm1 = [&](uint32_t it) {
+        for (int j = 0; j < S2_MT; ++j, ++n) {
+          const uint32_t stage = n & 1u;
+          mbar_wait(smem_u32(&acc1_free[j]), (it & 1u) ^ 1u);
+          mbar_wait(smem_u32(&a1_full[stage]), (n >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t dm = tmem_base + 64u * (uint32_t)j, dc = dm + 32u;
+          const uint32_t ab = a1_u + stage * S2_A1_STAGE;
+          uint32_t first_c = 0;
+#pragma unroll
+          for (int ps = 0; ps < 6; ++ps) {
+            const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);      // A split: 0,0,1,1,0,2
+            const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);      // W split: 0,1,0,1,2,0
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da = desc64(ab + sa * S2_A1_SPLIT + ks * 32, 512), db = desc64(wst_u + sw * 2048 + ks * 32, 512);
+              if (!((p.pass_mask >> ps) & 1)) continue;
+              if (ps == 0) mma_bf16(dm, da, db, idesc1, ks > 0);
+              else { mma_bf16(dc, da, db, idesc1, first_c); first_c = 1; }
+            }
+          }
+          mma_commit(smem_u32(&a1_empty[stage]));
+          mma_commit(smem_u32(&acc1_full[j]));
+        }
+      };
+      auto gemm2 = [&](uint32_t it) {
+        const uint32_t b = it & 1u;
+        mbar_wait(smem_u32(&acc2_free[b]), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait(smem_u32(halo_full), it & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t dm = tmem_base + ACC2_COL + 64u * b, dc = dm + 32u;
+        uint32_t first_m = 0, first_c = 0;
+        for (int tap = 0; tap < 9; ++tap) {
+          const int ky = tap / 3, kx = tap - ky * 3, px = kx & 1;
+          const uint32_t pw = px ? 8u : 9u;
+          const uint32_t aoff = ((uint32_t)s2_plane_off(ky & 1, px) + (uint32_t)(ky >> 1) * pw + (uint32_t)(kx >> 1)) * 64u;
+          const uint32_t sbo = pw * 64u;
+#pragma unroll
+          for (int ps = 0; ps < 6; ++ps) {
+            const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);
+            const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              const uint64_t da = desc64(pl_u + sa * S2_PLANE_BYTES + aoff + ks * 32, sbo);
+              const uint64_t db = desc64(w2_u + sw * w2_split + tap * w2_tap + ks * 32, 512);
+              if (!((p.pass_mask >> (ps + 8)) & 1)) continue;
+              if (ps == 0) { mma_bf16(dm, da, db, idesc2, first_m); first_m = 1; }
+              else { mma_bf16(dc, da, db, idesc2, first_c); first_c = 1; }
+            }
+          }
+        }
+        mma_commit(smem_u32(halo_free));
+        mma_commit(smem_u32(&acc2_full[b]));
+      };
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        if (it == 0) gemm1(0);
+        if (tile + (int)gridDim.x < tiles) gemm1(it + 1);       // next tile's stem GEMMs, paced by acc1_free
+        gemm2(it);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ===============================
+    const int q4 = warp & 3, half = warp >> 2;                 // TMEM lane quarter, column half
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const uint32_t pl_u = smem_u32(planes);
+    auto out_epi = [&](uint32_t it, int tile) {
+      const uint32_t b = it & 1u;
+      mbar_wait(smem_u32(&acc2_full[b]), (it >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int bi = tile / per_img, rem = tile - bi * per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int r = q4 * 32 + lane;
+      const int y = ty * S2_TH + (r >> 3), x = tx * S2_TW + (r & 7);
+      const int ncol = p.N2 >> 1;                               // columns per half: 8 (N2 = 16) or 16 (N2 = 32)
+      for (int c0 = 0; c0 < ncol; c0 += 8) {
+        uint32_t m[8], k[8];
+        const uint32_t col = ACC2_COL + 64u * b + (uint32_t)(half * ncol + c0);
+        tmem_ld8(lane_addr + col, m);
+        tmem_ld8(lane_addr + col + 32u, k);
+        tmem_ld_wait();
+        const int nn = half * ncol + c0;
+        if (y < p.Ho && x < p.Wo) {
+          float* dst = p.out + (((size_t)bi * p.Ho + y) * p.Wo + x) * p.Cout + nn;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            if (nn + 4 * g < p.Cout) {
+              const float4 bia = __ldg(reinterpret_cast<const float4*>(p.bias2 + nn + 4 * g));
+              float4 o;
+              o.x = act_fn(__uint_as_float(m[4 * g + 0]) + __uint_as_float(k[4 * g + 0]) + bia.x, p.act);
+              o.y = act_fn(__uint_as_float(m[4 * g + 1]) + __uint_as_float(k[4 * g + 1]) + bia.y, p.act);
+              o.z = act_fn(__uint_as_float(m[4 * g + 2]) + __uint_as_float(k[4 * g + 2]) + bia.z, p.act);
+              o.w = act_fn(__uint_as_float(m[4 * g + 3]) + __uint_as_float(k[4 * g + 3]) + bia.w, p.act);
+              *reinterpret_cast<float4*>(dst + 4 * g) = o;
+            }
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc2_free[b]));
+    };
+    uint32_t it = 0;
+    int prev_tile = -1;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int rem = tile % per_img;
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      const int sy0 = 2 * S2_TH * ty - 1, sx0 = 2 * S2_TW * tx - 1;
+      for (int j = 0; j < S2_MT; ++j) {
+        mbar_wait(smem_u32(&acc1_full[j]), it & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t m[16], k[16];
+        tmem_ld16(lane_addr + 64u * (uint32_t)j + 16u * (uint32_t)half, m);
+        tmem_ld16(lane_addr + 64u * (uint32_t)j + 32u + 16u * (uint32_t)half, k);
+        tmem_ld_wait();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&acc1_free[j]));
+        if (j == 0) mbar_wait(smem_u32(halo_free), (it & 1u) ^ 1u);   // conv2 of the previous tile has read the halo
+        const int q = j * 128 + q4 * 32 + lane;
+        if (q < S2_HPIX) {
+          const int hy = q / S2_HW, hx = q - hy * S2_HW;
+          const int sy = sy0 + hy, sx = sx0 + hx;
+          const bool in_img = sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;      // outside = conv2's zero padding
+          uint32_t o1[8], o2[8], o3[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float a = fmaxf(__uint_as_float(m[2 * c]) + __uint_as_float(k[2 * c]), 0.f);          // bias rides in the GEMM (k = 27)
+            float b = fmaxf(__uint_as_float(m[2 * c + 1]) + __uint_as_float(k[2 * c + 1]), 0.f);
+            if (!in_img) { a = 0.f; b = 0.f; }
+            split3(a, b, o1[c], o2[c], o3[c]);
+          }
+          const int py = hy & 1, px = hx & 1;
+          const uint32_t pix = (uint32_t)s2_plane_off(py, px) + (uint32_t)(hy >> 1) * (px ? 8u : 9u) + (uint32_t)(hx >> 1);
+          const uint32_t row = pl_u + pix * 64u;
+          const uint32_t sw = (row >> 7) & 3u;
+          const uint32_t d0 = (row - pl_u) + ((((uint32_t)(2 * half)) ^ sw) << 4), d1 = (row - pl_u) + ((((uint32_t)(2 * half + 1)) ^ sw) << 4);
+          *reinterpret_cast<uint4*>(planes + d0) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+          *reinterpret_cast<uint4*>(planes + d1) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+          *reinterpret_cast<uint4*>(planes + S2_PLANE_BYTES + d0) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+          *reinterpret_cast<uint4*>(planes + S2_PLANE_BYTES + d1) = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+          *reinterpret_cast<uint4*>(planes + 2 * S2_PLANE_BYTES + d0) = make_uint4(o3[0], o3[1], o3[2], o3[3]);
+          *reinterpret_cast<uint4*>(planes + 2 * S2_PLANE_BYTES + d1) = make_uint4(o3[4], o3[5], o3[6], o3[7]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(halo_full));
+      if (prev_tile >= 0) out_epi(it - 1, prev_tile);         // runs while the tensor core works on this tile's conv2
+      prev_tile = tile;
+    }
+    if (prev_tile >= 0) out_epi(it - 1, prev_tile);
+  }
+
+  // ---- teardown
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == S2_MMA_WARP) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static size_t stem2_smem_bytes(int N2) {
+  return (size_t)27 * N2 * 64 + S2_WST_BYTES + 2 * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 + 1024;
+}
+
+bool stem2_supported(const ConvParams& c) {
+  const int N2 = (c.Cout + 15) / 16 * 16;
+  return c.KS == 3 && c.stride == 2 && c.Cin == 32 && (c.Cout & 3) == 0 && N2 <= 32 && (c.Win & 3) == 0 &&
+         (reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && stem2_smem_bytes(N2) <= (size_t)227 * 1024 && !c.res && !c.up &&
+         c.anchors <= 1 && c.bias != nullptr;
+}
+
+// c: geometry of the SECOND conv as set up by engine.cu for YL_OP_STEM2 (Hin/Win = network input size, Hout/Wout = conv2 output)
+int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st) {
+  Stem2Params p{};
+  p.in = c.in; p.wimg = wimg; p.bias2 = c.bias; p.out = c.out;
+  p.B = c.B; p.H = c.Hin; p.W = c.Win;
+  p.Hs = (c.Hin + 2 - 3) / 2 + 1; p.Ws = (c.Win + 2 - 3) / 2 + 1;
+  p.Ho = c.Hout; p.Wo = c.Wout; p.Cout = c.Cout; p.N2 = (c.Cout + 15) / 16 * 16; p.act = c.act;
+  YL_REQUIRE(stem2_supported(c), "shape does not fit the fused stem kernel");
+  p.tiles_x = (p.Wo + S2_TW - 1) / S2_TW;
+  p.tiles_y = (p.Ho + S2_TH - 1) / S2_TH;
+  const long long nt = (long long)p.B * p.tiles_x * p.tiles_y;
+  YL_REQUIRE(nt < (1ll << 31) && (long long)p.B * p.Ho * p.Wo * p.Cout < (1ll << 40), "too many tiles");
+  p.num_tiles = (int)nt;
+  static const int mask_env = [] { const char* e = getenv("YL_S2_PASSES"); return e ? (int)strtol(e, nullptr, 0) : 0x3F3F; }();
+  p.pass_mask = mask_env;
+  const size_t smem = stem2_smem_bytes(p.N2);
+  static thread_local bool attr_set = false;
+  if (!attr_set) {
+    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  int gx = sm_count < p.num_tiles ? sm_count : p.num_tiles;
+  stem2_kernel<<<gx, S2_THREADS, smem, st>>>(p);
+  YL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace yl

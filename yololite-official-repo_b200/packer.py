@@ -106,7 +106,7 @@ class Program:
     vmap: Dict[int, int] = field(default_factory=dict)    # virtual id -> physical buffer id
 
     def add_blob(self, arr: np.ndarray) -> int:
-        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)
+        arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)      # float32 views (bf16 pairs) keep their bits
         off = self.blob_len
         pad = (-arr.size) % 64                        # keep every array 256-byte aligned
         self.blob.append(arr)
@@ -178,6 +178,51 @@ def tc_image(wm: np.ndarray, n_out: int) -> np.ndarray:
     return out.reshape(-1)
 
 
+def bf16_split3(x: np.ndarray):
+    """x (fp32) -> three uint16 arrays of bf16 bit patterns with x ~= b1 + b2 + b3 (each round-to-nearest-even), the
+    error-compensated operand format of the fused stem kernel (csrc/stem_kernel.cu)."""
+    def rn(v):
+        u = np.ascontiguousarray(v, np.float32).view(np.uint32).astype(np.uint64)
+        r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32)
+        return r.astype(np.uint16), (r << 16).astype(np.uint32).view(np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    b1, f1 = rn(x)
+    r1 = (x - f1).astype(np.float32)
+    b2, f2 = rn(r1)
+    b3, _ = rn((r1 - f2).astype(np.float32))
+    return b1, b2, b3
+
+
+def _sw64_rows(m: np.ndarray) -> np.ndarray:
+    """[rows][32] uint16 -> the K-major SWIZZLE_64B image: row r holds four 16 B chunks, chunk c at position c ^ ((r >> 1) & 3)."""
+    rows = m.shape[0]
+    t = m.reshape(rows, 4, 8)
+    out = np.empty_like(t)
+    r = np.arange(rows)
+    for c in range(4):
+        out[r, c ^ ((r >> 1) & 3), :] = t[r, c, :]
+    return out.reshape(rows, 32)
+
+
+def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
+    """Weight image of the fused stem kernel as float32 words (two bf16 per word, bits preserved):
+    [3 splits][9 taps][ceil16(n_out)][32 ch] conv2 weights, then [3 splits][32 stem ch][32 k] stem weights where
+    k = (ky*3 + kx)*3 + ci for k < 27, k = 27 is the folded BN bias (multiplied by a constant-1 column), k > 27 zero.
+    w2m: [288][>= n_out] with k = (ky*3 + kx)*32 + ci; ws: [27][32]; b0: [32]."""
+    n2 = (n_out + 15) // 16 * 16
+    w2 = np.zeros((9, n2, 32), np.float32)
+    w2[:, :n_out, :] = np.asarray(w2m, np.float64)[:, :n_out].reshape(9, 32, n_out).transpose(0, 2, 1).astype(np.float32)
+    st = np.zeros((32, 32), np.float32)
+    st[:, :27] = np.asarray(ws, np.float64).T.astype(np.float32)
+    st[:, 27] = np.asarray(b0, np.float64).astype(np.float32)
+    parts = []
+    for sp in bf16_split3(w2):
+        parts.append(np.concatenate([_sw64_rows(sp[t]) for t in range(9)]).reshape(-1))
+    for sp in bf16_split3(st):
+        parts.append(_sw64_rows(sp).reshape(-1))
+    return np.concatenate(parts).astype(np.uint16).view(np.float32)
+
+
 def _pad4(b: np.ndarray) -> np.ndarray:
     out = np.zeros(((b.size + 3) // 4 * 4,), np.float64)
     out[:b.size] = b
@@ -191,13 +236,13 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     P = Program(cfg=cfg)
 
     def emit(kind, src: Optional[_T], cout, red, k=1, stride=1, act=L.ACT_NONE, w=None, b=None, res: Optional[_T] = None,
-             up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0) -> Optional[_T]:
+             up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0, w3=None) -> Optional[_T]:
         dst = None if level is not None else P.new(cout, red)
         P.ops.append(dict(kind=kind, src=(-1 if src is None else src.vid), dst=(-(1 + level) if level is not None else dst.vid),
                           res=(-1 if res is None else res.vid), up=(-1 if up is None else up.vid),
                           cin=(3 if src is None else src.C), cout=cout, k=k, stride=stride, act=act, anchors=anchors, k2=k2,
                           w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
-                          w2_off=(-1 if w2 is None else P.add_blob(w2)),
+                          w2_off=(-1 if w2 is None else P.add_blob(w2)), w3_off=(-1 if w3 is None else P.add_blob(w3)),
                           wt_off=(P.add_blob(tc_image(np.asarray(w, np.float64).reshape(-1, w.shape[-1]), cout))
                                   if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW, L.OP_STEM2) and cout >= 8 and w.shape[0] >= 8 else -1)))
         return dst
@@ -232,7 +277,9 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         key = bb + "blocks.0.0"
         w1 = sd.get(key + ".conv.weight")
         s1, b1 = sd.bn(key + ".bn1")
-        x = emit(L.OP_STEM2, None, int(w1.shape[0]), 4, k=3, stride=2, act=L.ACT_RELU, w=_gemm_w(w1 * s1[:, None, None, None]),
+        w1m = _gemm_w(w1 * s1[:, None, None, None])
+        x = emit(L.OP_STEM2, None, int(w1.shape[0]), 4, k=3, stride=2, act=L.ACT_RELU, w=w1m,
+                 w3=stem2_image(w1m, int(w1.shape[0]), ws, b0) if int(w1.shape[0]) <= 32 else None,
                  b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
         feats = [_T(-1, stem_c, 2)]
         red = 4
@@ -377,7 +424,7 @@ def to_c(P: Program):
     for i, op in enumerate(P.ops):
         o = arr[i]
         for f in ("kind", "src", "dst", "res", "up", "cin", "cout", "k", "stride", "act", "anchors", "k2", "w_off", "b_off",
-                  "w2_off", "wt_off"):
+                  "w2_off", "wt_off", "w3_off"):
             setattr(o, f, int(op[f]))
     blob = np.concatenate(P.blob).astype(np.float32, copy=False)
     assert blob.size == P.blob_len
