@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define YL_ABI_VERSION 2
+#define YL_ABI_VERSION 3
 
 typedef struct yl_engine yl_engine;
 
@@ -37,8 +37,10 @@ enum yl_op_kind {
   YL_OP_CONV = 1,  /* dense KxK conv as implicit GEMM, NHWC -> NHWC; K=1 is the pointwise conv; epilogue:
                       +bias, +residual buffer, +nearest-upsampled coarser buffer, act, head layout       */
   YL_OP_DW = 2,    /* depthwise KxK conv (K = 3 or 5), NHWC, +bias, act                                   */
-  YL_OP_DWPW = 3,  /* fused DWConvBlock: depthwise 3x3 s1 (no bias) -> pointwise + bias + act
-                      (model_v2.py:23-39); the depthwise result never leaves shared memory               */
+  YL_OP_DWPW = 3,  /* fused depthwise k2 x k2 (3 or 5, stride 1, +bias b2, act2) -> pointwise + bias + residual + act;
+                      the depthwise result never leaves shared memory.  Covers DWConvBlock (model_v2.py:23-39: 3x3, no
+                      bias, no act2) and the dw_start -> pw_exp / dw_mid -> pw_proj pairs of timm's
+                      UniversalInvertedResidual (backbone called at model_v2.py:266-272)                   */
   YL_OP_STEM2 = 4  /* fused conv_stem (3x3 s2, Cin=3, NCHW input, 32 ch, +bias+ReLU) -> dense 3x3 s2 conv + bias + act
                       (timm blocks.0.0): the stem activation (13 MB/image at 640 px) never leaves shared memory.
                       cin = 3, cout = channels of the second conv, k/stride/act = the second conv's, k2 = stem
@@ -59,7 +61,7 @@ typedef struct yl_op {
   int32_t k, stride; /* padding is k/2 */
   int32_t act;       /* yl_act */
   int32_t anchors;   /* >0 only for head output convs: cout = anchors*(5+C), stored [B,A,H,W,5+C] */
-  int32_t k2;        /* YL_OP_DWPW: depthwise kernel size (3); otherwise 0 */
+  int32_t k2;        /* YL_OP_DWPW: depthwise kernel size (3 or 5); YL_OP_STEM2: stem channels; otherwise 0 */
   int64_t w_off;     /* float offset of the GEMM/stencil weights in the blob */
   int64_t b_off;     /* float offset of the bias (cout floats), or -1 */
   int64_t w2_off;    /* YL_OP_DWPW: float offset of depthwise weights [k2*k2][cin]; otherwise -1 */
@@ -68,6 +70,9 @@ typedef struct yl_op {
   int64_t w3_off;    /* YL_OP_STEM2: float offset of the bf16-triple weight image of the fused stem kernel
                         ([3 splits][9 taps][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
                         row 64 B, SWIZZLE_64B K-major, two bf16 per float slot), or -1 (older tf32 kernel) */
+  int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1 */
+  int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv */
+  int32_t reserved;  /* must be 0 */
 } yl_op;
 
 /* Build an engine on `device` from a layer program and a HOST weight blob.

@@ -18,7 +18,7 @@ from yololite_b200 import _lib as L, packer  # noqa: E402
 KINDS = {"stem": 0, "conv": 1, "dw": 2, "dwpw": 3, "stem2": 4}
 
 
-def build(kind, cin, cout, k, stride, act, up, res):
+def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0):
     g = np.random.RandomState(0)
     blob, off = [], [0]
 
@@ -34,7 +34,7 @@ def build(kind, cin, cout, k, stride, act, up, res):
     op = L.YlOp()
     op.kind, op.k, op.stride, op.act, op.anchors = KINDS[kind], k, stride, act, 0
     op.src, op.dst, op.res, op.up = 0, 1, (2 if res else -1), (3 if up else -1)
-    op.k2, op.w2_off, op.wt_off, op.w3_off = 0, -1, -1, -1
+    op.k2, op.w2_off, op.wt_off, op.w3_off, op.b2_off, op.act2 = 0, -1, -1, -1, -1, 0
     op.cin, op.cout = cin, cout
     if kind == "dw":
         op.w_off = add(g.randn(k * k, cin) / k)
@@ -57,8 +57,9 @@ def build(kind, cin, cout, k, stride, act, up, res):
         op.w_off = add(wm)
         op.wt_off = add(packer.tc_image(wm, cout))
         if kind == "dwpw":
-            op.k, op.k2 = 1, 3
-            op.w2_off = add(g.randn(9, cin) / 3)
+            op.k, op.k2, op.act2 = 1, k2, act2
+            op.w2_off = add(g.randn(k2 * k2, cin) / k2)
+            op.b2_off = add(packer._pad4(g.randn(cin) * 0.3))
     op.b_off = add(packer._pad4(g.randn(cout)))
     return op, torch.from_numpy(np.concatenate(blob)).cuda()
 
@@ -76,10 +77,12 @@ def main():
     ap.add_argument("--up", type=int, default=0)
     ap.add_argument("--res", type=int, default=0)
     ap.add_argument("--tc", type=int, default=1)
+    ap.add_argument("--k2", type=int, default=3)
+    ap.add_argument("--act2", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     lib = L.lib()
-    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res)
+    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res, a.k2, a.act2)
     B, H = a.batch, a.hw
     k = op.k
     ho = (H + 2 * (k // 2) - k) // a.stride + 1
@@ -106,7 +109,7 @@ def main():
     ms = e0.elapsed_time(e1) / a.iters
     nbytes = 4 * (x.numel() + out.numel() + (res.numel() if res is not None else 0) + (up.numel() if up is not None else 0))
     print(json.dumps({"kind": a.kind, "cin": a.cin, "cout": a.cout, "k": a.k, "stride": a.stride, "hw": H, "B": B, "tc": a.tc,
-                      "up": a.up, "res": a.res, "ms": ms, "GBps": nbytes / ms / 1e6}))
+                      "up": a.up, "res": a.res, "k2": a.k2, "ms": ms, "GBps": nbytes / ms / 1e6}))
 
 
 if __name__ == "__main__":

@@ -23,12 +23,13 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), name
     assert sorted(y.EXPORTS) == decl
-    assert lib.yl_abi_version() == 2
+    assert lib.yl_abi_version() == 3
 
 
 def test_op_struct_layout_matches_header():
     from yololite_b200 import _lib as L
-    assert ctypes.sizeof(L.YlOp) == 12 * 4 + 4 * 8
+    assert ctypes.sizeof(L.YlOp) == 12 * 4 + 6 * 8 + 2 * 4
+    assert L.YlOp.b2_off.offset == 88 and L.YlOp.act2.offset == 96
     assert L.YlOp.w_off.offset == 48
 
 

@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 TOL = 2e-4
 
 
-def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, w2=None, use_tc=1, nchw_input=False):
+def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, w2=None, use_tc=1, nchw_input=False,
+         b2=None, act2=0):
     """w: [Cout,Cin,k,k] torch fp32 (dense) or [C,1,k,k] (depthwise); returns NHWC output (or head layout)."""
     from yololite_b200 import _lib as L, packer
     lib = L.lib()
@@ -32,7 +33,7 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
     op = L.YlOp()
     op.kind, op.k, op.stride, op.act, op.anchors = kind, k, stride, act, anchors
     op.src, op.dst, op.res, op.up = 0, 1, (2 if res is not None else -1), (3 if up is not None else -1)
-    op.k2, op.w2_off, op.wt_off, op.w3_off = 0, -1, -1, -1
+    op.k2, op.w2_off, op.wt_off, op.w3_off, op.b2_off, op.act2 = 0, -1, -1, -1, -1, 0
     if kind == L.OP_DW:
         op.cin = op.cout = cout
         op.w_off = add(np.transpose(wn, (2, 3, 1, 0)).reshape(k * k, cout))
@@ -46,8 +47,11 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
         op.w_off = add(wm)
         op.wt_off = add(packer.tc_image(wm, cout))
         if kind == L.OP_DWPW:
-            op.k, op.k2 = 1, 3
-            op.w2_off = add(np.transpose(w2.double().numpy(), (2, 3, 1, 0)).reshape(9, -1))
+            op.k, op.k2 = 1, int(w2.shape[-1])
+            op.w2_off = add(np.transpose(w2.double().numpy(), (2, 3, 1, 0)).reshape(op.k2 * op.k2, -1))
+            op.act2 = act2
+            if b2 is not None:
+                op.b2_off = add(packer._pad4(b2.double().numpy()))
     op.b_off = add(packer._pad4(bias.double().numpy())) if bias is not None else -1
     dblob = torch.from_numpy(np.concatenate(blob)).cuda()
     xin = x_nhwc.cuda().contiguous()
@@ -162,6 +166,29 @@ def test_fused_dw_pw(use_tc, c, hw):
     got = _run(3, x, wp, b, 1, 1, 1, w2=wd, use_tc=use_tc)
     mid = F.conv2d(x.permute(0, 3, 1, 2), wd, None, padding=1, groups=c)
     want = _ref(mid, wp, b, 1, 1, 1)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("cin,cout,k2,h,w,res", [(96, 48, 3, 40, 40, True), (48, 192, 3, 40, 40, False), (256, 64, 5, 20, 20, True),
+                                                 (256, 64, 3, 20, 20, True), (192, 64, 5, 20, 20, True), (64, 256, 5, 20, 20, False),
+                                                 (32, 96, 5, 80, 80, False), (48, 288, 3, 23, 37, False), (288, 64, 3, 7, 9, True),
+                                                 (64, 64, 5, 3, 2, True)])
+def test_fused_dw_pw_uir(use_tc, cin, cout, k2, h, w, res):
+    """The dw_start -> pw_exp / dw_mid -> pw_proj (+residual) pairs of the backbone's UIR blocks: depthwise 3x3 / 5x5 with
+    its own folded-BN bias and ReLU, pointwise with bias; large-K shapes stream the weight slabs (tcgen05 path)."""
+    g = torch.Generator().manual_seed(cin + cout + k2)
+    x = torch.randn(2, h, w, cin, generator=g)
+    wd = torch.randn(cin, 1, k2, k2, generator=g) / k2
+    bd = torch.randn(cin, generator=g) * 0.5
+    wp = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(2, h, w, cout, generator=g) if res else None
+    act2, act = (1, 0) if res else (0, 1)                 # dw_mid: ReLU then linear projection; dw_start: linear then ReLU
+    got = _run(3, x, wp, b, 1, 1, act, w2=wd, use_tc=use_tc, b2=bd, act2=act2, res=r)
+    mid = F.conv2d(x.permute(0, 3, 1, 2), wd, bd, padding=k2 // 2, groups=cin)
+    mid = F.relu(mid) if act2 else mid
+    want = _ref(mid, wp, b, 1, 1, act, res=r)
     assert float((got - want).abs().max()) <= TOL
 
 

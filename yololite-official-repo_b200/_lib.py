@@ -12,7 +12,15 @@ class YlOp(ctypes.Structure):
                 ("up", ctypes.c_int32), ("cin", ctypes.c_int32), ("cout", ctypes.c_int32), ("k", ctypes.c_int32),
                 ("stride", ctypes.c_int32), ("act", ctypes.c_int32), ("anchors", ctypes.c_int32),
                 ("k2", ctypes.c_int32), ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
-                ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64), ("w3_off", ctypes.c_int64)]
+                ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64), ("w3_off", ctypes.c_int64),
+                ("b2_off", ctypes.c_int64), ("act2", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+    def __init__(self, *args, **kw):
+        super().__init__(*args, **kw)
+        if not args:                      # optional blob offsets default to "absent", not to offset 0
+            for f in ("b_off", "w2_off", "wt_off", "w3_off", "b2_off"):
+                if f not in kw:
+                    setattr(self, f, -1)
 
 
 OP_STEM, OP_CONV, OP_DW, OP_DWPW, OP_STEM2 = 0, 1, 2, 3, 4

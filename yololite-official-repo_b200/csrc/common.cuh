@@ -61,11 +61,13 @@ struct ConvParams {
   const float* __restrict__ res;    // [M][N] or nullptr
   const float* __restrict__ up;     // [B][Hu][Wu][N] or nullptr
   const float* __restrict__ w2;     // DWPW: depthwise weights [k2*k2][Cin]
+  const float* __restrict__ b2;     // DWPW: depthwise bias [Cin] or nullptr
   float* __restrict__ out;
   int B, Hin, Win, Cin, Hout, Wout, Cout;
   int KS, stride, pad;
   int Hu, Wu;
   int act;
+  int act2;                          // DWPW: activation between the depthwise and the pointwise stage
   int anchors;                       // >0: head layout [B,A,H,W,D], D = Cout/anchors
 };
 

@@ -98,7 +98,8 @@ int launch_stem(const ConvParams& p, cudaStream_t s) {
 constexpr int BM = 128, BK = 16, GEMM_THREADS = 256, TM = 8;
 
 // MODE 0: pointwise (A rows are contiguous), 1: generic KxK im2col gather,
-// MODE 2: fused DWConvBlock -- A[m][c] = depthwise3x3(in)[m][c] computed while loading (model_v2.py:23-39)
+// MODE 2: fused depthwise -> pointwise -- A[m][c] = act2(depthwiseKxK(in)[m][c] + b2[c]) computed while loading
+//         (DWConvBlock model_v2.py:23-39; dw_start/dw_mid -> pointwise pairs of the backbone's UIR blocks)
 template <int TN, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(ConvParams p, int ldw) {
   constexpr int BN = 16 * TN;
@@ -147,22 +148,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) conv_gemm_kernel(ConvParams p, i
         if (MODE == 0) {
           v = __ldg(reinterpret_cast<const float4*>(a_base[i] + k));
         } else if (MODE == 2) {
-#pragma unroll
-          for (int ky = 0; ky < 3; ++ky) {
+          if (p.b2) v = __ldg(reinterpret_cast<const float4*>(p.b2 + k));
+          for (int ky = 0; ky < p.KS; ++ky) {
             const int iy = a_oy[i] + ky;
             if (iy < 0 || iy >= p.Hin) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
+            for (int kx = 0; kx < p.KS; ++kx) {
               const int ix = a_ox[i] + kx;
               if (ix < 0 || ix >= p.Win) continue;
               const float4 x4 = __ldg(reinterpret_cast<const float4*>(a_base[i] + ((size_t)iy * p.Win + ix) * p.Cin + k));
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w2 + (ky * 3 + kx) * p.Cin + k));
+              const float4 w4 = __ldg(reinterpret_cast<const float4*>(p.w2 + (ky * p.KS + kx) * p.Cin + k));
               v.x = fmaf(x4.x, w4.x, v.x);
               v.y = fmaf(x4.y, w4.y, v.y);
               v.z = fmaf(x4.z, w4.z, v.z);
               v.w = fmaf(x4.w, w4.w, v.w);
             }
           }
+          v.x = act_fn(v.x, p.act2); v.y = act_fn(v.y, p.act2); v.z = act_fn(v.z, p.act2); v.w = act_fn(v.w, p.act2);
         } else {
           const int tap = k / p.Cin, ci = k - tap * p.Cin;
           const int ky = tap / p.KS, kx = tap - ky * p.KS;
@@ -318,7 +319,7 @@ static int launch_conv_gemm_tn(const ConvParams& p, int ldw, cudaStream_t s) {
 }
 
 int launch_dwpw(const ConvParams& p, cudaStream_t s) {
-  YL_REQUIRE(p.w2 && p.KS == 3 && p.stride == 1 && p.pad == 1, "fused DWConvBlock is depthwise 3x3 s1 p1 + pointwise");
+  YL_REQUIRE(p.w2 && (p.KS == 3 || p.KS == 5) && p.stride == 1 && p.pad == p.KS / 2, "fused depthwise (3x3 / 5x5, s1) + pointwise");
   YL_REQUIRE(p.Hin == p.Hout && p.Win == p.Wout, "fused DWConvBlock keeps the spatial size");
   return launch_conv_gemm(p, s);
 }

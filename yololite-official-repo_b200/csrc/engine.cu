@@ -40,7 +40,7 @@ struct yl_engine {
 namespace yl {
 
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
-bool tc_plan(int K, int N, int anchors, int mode, int* Nc, int* nchunks, int* stages, int* halo_slots);
+bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout);
 bool stem2_supported(const ConvParams& c);
 int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st);
 
@@ -58,7 +58,11 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   p.KS = op.k; p.stride = op.stride; p.pad = op.k / 2;
   p.Hu = hu; p.Wu = wu;
   p.act = op.act; p.anchors = op.anchors;
-  if (op.kind == YL_OP_DWPW) { p.KS = op.k2; p.pad = op.k2 / 2; }     // geometry of the depthwise stage
+  if (op.kind == YL_OP_DWPW) {                                        // geometry / epilogue of the depthwise stage
+    p.KS = op.k2; p.pad = op.k2 / 2;
+    p.b2 = op.b2_off >= 0 ? blob + op.b2_off : nullptr;
+    p.act2 = op.act2;
+  }
   if (op.kind == YL_OP_STEM2) {
     p.Cin = op.k2;                                // K of the second conv = 9 * stem channels
     ++g_tc_launches;
@@ -69,11 +73,10 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {
     const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
     const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
-    int nc, nch, stg, hs;
     // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
     // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
     const bool big = (K >= 32 && op.cout >= 32) || use_tc == 2;
-    if (big && tc_plan(K, op.cout, op.anchors, mode, &nc, &nch, &stg, &hs) && (op.cin & 3) == 0)
+    if (big && (op.cin & 3) == 0 && tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout))
     { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
   }
   ++g_simt_launches;
@@ -183,6 +186,9 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
     YL_REQUIRE(op.kind != YL_OP_STEM2 || (op.wt_off >= 0 && op.w2_off >= 0 && op.k2 == 32 && op.k == 3 && op.stride == 2),
                "YL_OP_STEM2 needs the tcgen05 weight image, stem weights, 32 stem channels and a 3x3 s2 second conv");
     YL_REQUIRE(op.k >= 1 && (op.k & 1) && op.stride >= 1 && op.cin >= 1 && op.cout >= 1, "bad conv geometry");
+    YL_REQUIRE(op.kind != YL_OP_DWPW || ((op.k2 == 3 || op.k2 == 5) && op.k == 1 && op.stride == 1 && op.w2_off >= 0 &&
+                                         op.b2_off < (int64_t)blob_floats && op.act2 >= YL_ACT_NONE && op.act2 <= YL_ACT_SILU),
+               "YL_OP_DWPW: depthwise 3x3 or 5x5 stride 1 followed by a pointwise conv");
     YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
     YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
     YL_REQUIRE((op.w_off & 3) == 0 && (op.b_off < 0 || (op.b_off & 3) == 0), "blob offsets must be 16-byte aligned");

@@ -19,7 +19,10 @@
 //              coarser level + ReLU/SiLU, 16 B stores (head layout [B,A,S,S,5+C] written directly).
 // The weight image (hi and lo, pre-split and pre-swizzled on the host) stays resident in shared memory for the
 // CTA's lifetime.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
+#include <cuda.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -28,14 +31,14 @@ namespace yl {
 constexpr int TC_PROD_WARPS = 8;                 // producer warps
 constexpr int TC_EPI_WARP0 = 8;                  // epilogue warps 8..11 (warp % 4 == TMEM lane quarter)
 constexpr int TC_MMA_WARP = 12;
-constexpr int TC_THREADS = 32 * 13;
+constexpr int TC_TMA_WARP = 13;                  // MODE 2: one thread issues the halo tile loads (cp.async.bulk.tensor) and W slabs
+constexpr int TC_THREADS = 32 * 14;
+constexpr int TC_MAX_HALO_SLOTS = 4;
 constexpr int TC_BM = 128;
 constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one K-slab (32 fp32) of the A tile
 constexpr int TC_SMEM_BUDGET = 226 * 1024;      // of the 227 KB a CTA may use
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // MODE 2 spatial tile = 128 output pixels
-constexpr int TC_HALO_W = TC_TILE_W + 2, TC_HALO_PIX = (TC_TILE_H + 2) * (TC_TILE_W + 2);
-constexpr int TC_HALO_BYTES = TC_HALO_PIX * 128;     // one 32-channel slab of the halo tile
+constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // MODE 3 spatial tile = 128 output pixels (MODE 2 picks its own, see tc_plan)
 // MODE 3 (stem 3x3 s2 on the NCHW input -> 3x3 s2 conv): per 8x16 output tile the stem output halo is 17x33 pixels x 32 ch,
 // computed from a 3 x 35 x 67 input patch
 constexpr int S3_HALO_H = 2 * TC_TILE_H + 1, S3_HALO_W = 2 * TC_TILE_W + 1, S3_HALO_PIX = S3_HALO_H * S3_HALO_W;
@@ -43,16 +46,20 @@ constexpr int S3_PATCH_H = 2 * S3_HALO_H + 1, S3_PATCH_W = 2 * S3_HALO_W + 1, S3
 constexpr int S3_PATCH_BYTES = 3 * S3_PATCH_H * S3_PATCH_PITCH * 4;      // 28560
 constexpr int S3_HALO_BYTES = S3_HALO_PIX * 128;                        // 71808
 constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
-constexpr int TC_AUX_BYTES = 128 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
+constexpr int TC_AUX_BYTES = 256 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
 
 struct TcParams {
   ConvParams c;
   const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
-  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise3x3->pointwise
+  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise KSxKS -> pointwise, 3 stem -> 3x3 s2 (older tf32 kernel)
   int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
   int Hs, Ws;           // MODE 3: stem output size
   int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
   int halo_slots;       // MODE 2: halo ring depth
+  int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
+  int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
+  int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
+                        // streamed from L2 into the A stage's own W slot with cp.async.bulk
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
   int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
   long long M;
@@ -175,8 +182,8 @@ __device__ __forceinline__ float4 load_a(const ConvParams& c, const float* rbase
   return a;
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
+template <int MODE, int KS>
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,29 +192,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 
   // ---- shared memory carve-up (all slabs 1024 B aligned)
   const uint32_t w_slab_bytes = (uint32_t)p.Nc * 128u;
+  // resident weights: [hi: nslab slabs][lo: nslab slabs]; streamed (MODE 2, p.wstream): stages x (hi slab, lo slab)
+  const int w_slabs = (MODE == 2 && p.wstream) ? p.stages : p.nslab;
   unsigned char* w_hi = smem;
-  unsigned char* w_lo = w_hi + (size_t)p.nslab * w_slab_bytes;
-  unsigned char* a_ring = w_lo + (size_t)p.nslab * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
-  unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x 23 KB
+  unsigned char* w_lo = w_hi + (size_t)w_slabs * w_slab_bytes;
+  unsigned char* a_ring = w_lo + (size_t)w_slabs * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
+  unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x halo_bytes
   // MODE 3: `halo` region = stem weight image (hi 4 KB, lo 4 KB) | stem-output halo (71808 B) | input patch (28560 B)
-  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)9 * p.nslab * 32 * 4 : 0));
+  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * p.halo_bytes : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
+  // MODE 2: depthwise taps [KS*KS][nslab*32] followed by the depthwise bias row
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)(KS * KS + 1) * p.nslab * 32 * 4 : 0));
   uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
   uint64_t* empty_bar = bars + TC_MAX_STAGES;      // [stages]   MMA commit -> producers (count 1)
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA         (count 4)
   uint64_t* halo_full = tempty_bar + 2;            // MODE 3: epilogue (4 warps) -> producers: stem halo written
   uint64_t* halo_empty = tempty_bar + 3;           // MODE 3: producers (8 warps) -> epilogue: halo consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 4);
+  uint64_t* wfull_bar = tempty_bar + 4;            // [stages]   MODE 2 streamed weights: cp.async.bulk complete_tx -> MMA
+  uint64_t* hfull_bar = wfull_bar + TC_MAX_STAGES;   // [halo_slots] MODE 2: TMA complete_tx -> producers
+  uint64_t* hempty_bar = hfull_bar + TC_MAX_HALO_SLOTS;   // [halo_slots] MODE 2: producers (8 warps) -> TMA thread
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + TC_MAX_HALO_SLOTS);
   float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 rows x TC_EPI_PITCH floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { mbar_init(smem_u32(&full_bar[s]), TC_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), TC_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); mbar_init(smem_u32(&wfull_bar[s]), 1);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
     mbar_init(smem_u32(halo_full), 4);
     mbar_init(smem_u32(halo_empty), TC_PROD_WARPS);
+    for (int s = 0; s < TC_MAX_HALO_SLOTS; ++s) { mbar_init(smem_u32(&hfull_bar[s]), 1); mbar_init(smem_u32(&hempty_bar[s]), TC_PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -216,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   // resident weight image: hi then lo, every slab's rows [chunk_n0, chunk_n0+Nc)
-  {
+  if (!(MODE == 2 && p.wstream)) {
     const int per_slab4 = p.Nc * 8;                                 // float4 per slab
     const int total4 = 2 * p.nslab * per_slab4;
     for (int i = threadIdx.x; i < total4; i += TC_THREADS) {
@@ -233,9 +249,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
   }
   if (MODE == 2) {
     const int cp = p.nslab * 32;
-    for (int i = threadIdx.x; i < 9 * cp; i += TC_THREADS) {
+    for (int i = threadIdx.x; i < (KS * KS + 1) * cp; i += TC_THREADS) {
       const int tap = i / cp, k = i - tap * cp;
-      w2s[i] = k < p.K ? __ldg(c.w2 + tap * c.Cin + k) : 0.f;
+      float v = 0.f;
+      if (k < p.K) v = tap < KS * KS ? __ldg(c.w2 + tap * c.Cin + k) : (c.b2 ? __ldg(c.b2 + k) : 0.f);
+      w2s[i] = v;
     }
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -468,62 +486,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
         if (++c_stage == p.stages) c_stage = 0;
       }
     } else {
-      // fused DWConvBlock on spatial tiles of 8x16 output pixels.  Per K-slab the (8+2)x(16+2) halo of the INPUT is copied
-      // with cp.async into a small ring (zero-filled outside the image = the conv padding); after a producer-group
-      // barrier every thread computes the depthwise 3x3 for 4 horizontally adjacent pixels x 4 channels from shared
-      // memory (18 halo + 9 weight 16 B loads for 4 outputs), splits hi/lo and writes the A stage.
+      // fused depthwise -> pointwise on spatial tiles of tile_h x tile_w (<= 128) output pixels.  Per K-slab the
+      // (tile_h + KS - 1) x (tile_w + KS - 1) x 32-channel halo of the INPUT arrives in a ring slot as ONE TMA tile
+      // (cp.async.bulk.tensor.4d over the NHWC tensor, issued by the TMA warp; out-of-image pixels and channels past K
+      // are zero-filled by the hardware = the conv padding).  Every producer thread computes the depthwise KS x KS
+      // (+ bias, act2) for 4 horizontally adjacent pixels x 4 channels from shared memory, splits hi/lo and writes the
+      // A stage.  With p.wstream the K-slab of the pointwise weights travels with the A stage (cp.async.bulk from L2).
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
       const int HS = p.halo_slots;
-      const int per_img = p.tiles_x * p.tiles_y;
-      const int g = t >> 3, ty = g >> 2, tx0 = (g & 3) * 4;
+      const int TW = p.tile_w, HW = p.halo_w;
+      const int g = t >> 3;
+      int ty = (4 * g) / TW, tx0 = 4 * g - ty * TW;
+      if (4 * g >= TW * p.tile_h) { ty = 0; tx0 = 0; }             // rows past the tile: recompute pixel 0, never stored
+      const int arow0 = 4 * g;
       const int cp = p.nslab * 32;
-      int issued = 0, i_tile = blockIdx.x, i_s = 0, i_slot = 0;
-      auto issue = [&]() {
-        if (issued < total) {
-          const int b = i_tile / per_img, rem = i_tile - b * per_img;
-          const int y0 = (rem / p.tiles_x) * TC_TILE_H - 1, x0 = (rem % p.tiles_x) * TC_TILE_W - 1;
-          const uint32_t dst = smem_u32(halo) + (uint32_t)i_slot * TC_HALO_BYTES;
-          const float* img = c.in + (size_t)b * c.Hin * c.Win * c.Cin + i_s * 32;
-          for (int idx = t; idx < TC_HALO_PIX * 8; idx += 256) {
-            const int pix = idx >> 3, hc = idx & 7;
-            const int hy = pix / TC_HALO_W, hx = pix - hy * TC_HALO_W;
-            const int y = y0 + hy, x = x0 + hx;
-            const float* src = c.in;
-            uint32_t nbytes = 0;
-            if (y >= 0 && y < c.Hin && x >= 0 && x < c.Win && i_s * 32 + hc * 4 < p.K) {
-              src = img + ((size_t)y * c.Win + x) * c.Cin + hc * 4;
-              nbytes = 16;
-            }
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + (uint32_t)idx * 16u), "l"(src), "r"(nbytes) : "memory");
-          }
-          if (++i_s == p.nslab) { i_s = 0; i_tile += gridDim.x; }
-          if (++i_slot == HS) i_slot = 0;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");      // always commit: keeps the group count uniform
-        ++issued;
-      };
-      for (int j = 0; j < HS - 1; ++j) issue();
+      const uint32_t hoff = ((uint32_t)(ty * HW + tx0) * 8u + (uint32_t)ch) * 16u;
+      uint32_t soff[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = arow0 + i;
+        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+      }
       int stage = 0, c_slot = 0, c_s = 0;
-      uint32_t phase = 0;
+      uint32_t phase = 0, hphase = 0;
       for (int j = 0; j < total; ++j) {
-        if (HS == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");            // item j landed for everyone; slot of item j-1 is free
-        issue();                                                  // item j + HS - 1
-        const unsigned char* hb = halo + (size_t)c_slot * TC_HALO_BYTES + ((size_t)(ty * TC_HALO_W + tx0) * 8 + ch) * 16;
+        mbar_wait(smem_u32(&hfull_bar[c_slot]), hphase);          // this item's halo tile has landed
+        const unsigned char* hb = halo + (size_t)c_slot * p.halo_bytes + hoff;
         const float* wk = w2s + c_s * 32 + ch * 4;
         float4 a[4];
+        {
+          const float4 b4 = *reinterpret_cast<const float4*>(wk + KS * KS * cp);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int i = 0; i < 4; ++i) a[i] = b4;
+        }
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          float4 h[6];
+        for (int ky = 0; ky < KS; ++ky) {
+          float4 h[KS + 3];
 #pragma unroll
-          for (int x = 0; x < 6; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(ky * TC_HALO_W + x) * 128);
+          for (int x = 0; x < KS + 3; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(ky * HW + x) * 128);
 #pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wk + (ky * 3 + kx) * cp);
+          for (int kx = 0; kx < KS; ++kx) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wk + (ky * KS + kx) * cp);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               a[i].x = fmaf(h[i + kx].x, w4.x, a[i].x); a[i].y = fmaf(h[i + kx].y, w4.y, a[i].y);
@@ -531,19 +535,85 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
             }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hempty_bar[c_slot]));   // this warp no longer reads the slot
+        if (c.act2 == YL_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { a[i].x = fmaxf(a[i].x, 0.f); a[i].y = fmaxf(a[i].y, 0.f); a[i].z = fmaxf(a[i].z, 0.f); a[i].w = fmaxf(a[i].w, 0.f); }
+        } else if (c.act2) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = act4(a[i], c.act2);
+        }
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+        if (p.raw_hi) {          // the tensor core drops the low 13 mantissa bits of hi itself
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split_store(hi, hi + TC_SLAB_BYTES, ty * TC_TILE_W + tx0 + i, ch, a[i]);
+          for (int i = 0; i < 4; ++i) {
+            float4 l;
+            l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
+            l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
+            l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
+            l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(hi + soff[i]) = a[i];
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) split_store(hi, hi + TC_SLAB_BYTES, arow0 + i, ch, a[i]);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        if (++c_slot == HS) c_slot = 0;
+        if (++c_slot == HS) { c_slot = 0; hphase ^= 1; }
         if (++c_s == p.nslab) c_s = 0;
       }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
+  } else if (MODE == 2 && warp == TC_TMA_WARP) {
+    // =============================== TMA issuer (MODE 2) ===============================
+    if (lane == 0) {
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = my_tiles * p.nslab;
+      const int per_img = p.tiles_x * p.tiles_y;
+      constexpr int PAD = KS / 2;
+      int i_tile = blockIdx.x, i_s = 0, slot = 0, stage = 0;
+      int b = 0, y0 = 0, x0 = 0;
+      uint32_t hphase = 0, phase = 0;
+      for (int j = 0; j < total; ++j) {
+        if (i_s == 0) {
+          b = i_tile / per_img;
+          const int rem = i_tile - b * per_img;
+          y0 = (rem / p.tiles_x) * p.tile_h - PAD;
+          x0 = (rem % p.tiles_x) * p.tile_w - PAD;
+        }
+        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1);          // all producer warps are done with item j - HS
+        {
+          const uint32_t bar = smem_u32(&hfull_bar[slot]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.halo_bytes) : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(smem_u32(halo) + (uint32_t)slot * (uint32_t)p.halo_bytes), "l"(&tmap), "r"(i_s * 32), "r"(x0), "r"(y0), "r"(b), "r"(bar)
+              : "memory");
+        }
+        if (p.wstream) {
+          // the MMAs that read this stage's A and W slots (item j - stages) are done: refill the W slot from L2
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&wfull_bar[stage]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * w_slab_bytes) : "memory");
+#pragma unroll
+          for (int ps = 0; ps < 2; ++ps) {
+            const float* src = p.wimg + ((size_t)ps * p.nslab + i_s) * p.Npad * 32;
+            const uint32_t dst = smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(src), "r"(w_slab_bytes), "r"(bar) : "memory");
+          }
+        }
+        if (++i_s == p.nslab) { i_s = 0; i_tile += gridDim.x; }
+        if (++slot == p.halo_slots) { slot = 0; hphase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
   } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ===============================
     // Two accumulators per tile: `main` takes Ahi*Whi, `corr` takes Alo*Whi + Ahi*Wlo.  The tensor core truncates its fp32
@@ -589,8 +659,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_u32(a_ring + (size_t)stage * 2 * TC_SLAB_BYTES);
           const uint32_t a_lo = a_hi + TC_SLAB_BYTES;
-          const uint32_t b_hi = smem_u32(w_hi + (size_t)s * w_slab_bytes);
-          const uint32_t b_lo = smem_u32(w_lo + (size_t)s * w_slab_bytes);
+          uint32_t b_hi = smem_u32(w_hi + (size_t)s * w_slab_bytes);
+          uint32_t b_lo = smem_u32(w_lo + (size_t)s * w_slab_bytes);
+          if (MODE == 2 && p.wstream) {
+            mbar_wait(smem_u32(&wfull_bar[stage]), phase);     // this stage's W slabs have landed (async proxy write)
+            b_hi = smem_u32(w_hi) + (uint32_t)(stage * 2) * w_slab_bytes;
+            b_lo = b_hi + w_slab_bytes;
+          }
           const int ksteps = min(4, (p.K - s * 32 + 7) >> 3);
           for (int j = 0; j < ksteps; ++j) {
             const uint32_t ko = (uint32_t)j * 32u;          // 8 fp32 = 32 B along K inside the 128 B swizzle row
@@ -607,7 +682,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < TC_MMA_WARP) {
     // =============================== epilogue ===============================
     // TMEM -> registers (lane = row) -> padded smem transpose -> coalesced 16 B global accesses (lane = 4 columns,
     // 8 lanes per 128 B row segment): bias, residual and the upsampled coarser level are read with the same mapping.
@@ -631,12 +706,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
       if (MODE >= 2) {
         const int per_img = p.tiles_x * p.tiles_y;
         const int b = tile / per_img, rem = tile - b * per_img;
-        const int y0 = (rem / p.tiles_x) * TC_TILE_H, x0 = (rem % p.tiles_x) * TC_TILE_W;
+        const int TW = MODE == 2 ? p.tile_w : TC_TILE_W, TH = MODE == 2 ? p.tile_h : TC_TILE_H;
+        const int y0 = (rem / p.tiles_x) * TH, x0 = (rem % p.tiles_x) * TW;
+        int ry = (q * 32 + vr) / TW, rx = (q * 32 + vr) - ry * TW;      // rows vr + 4*it: step 4 pixels (TW % 4 == 0)
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
-          const int r = q * 32 + vr + 4 * it;
-          const int y = y0 + (r >> 4), x = x0 + (r & 15);
-          orow[it] = (y < c.Hout && x < c.Wout) ? ((b * c.Hout + y) * c.Wout + x) * N : -1;
+          const int y = y0 + ry, x = x0 + rx;
+          orow[it] = (ry < TH && y < c.Hout && x < c.Wout) ? ((b * c.Hout + y) * c.Wout + x) * N : -1;
+          rx += 4;
+          if (rx >= TW) { rx -= TW; ++ry; }
         }
       } else {
 #pragma unroll
@@ -829,37 +907,114 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(TcParams p) {
 // the image layout only ([2][nslab][Npad][32]), which does not depend on the chunking.
 static bool tc_dense_epi(int N, int anchors, int Nc, int nchunks) { return (N & 3) != 0 && anchors <= 1 && nchunks == 1 && Nc <= 128; }
 
-bool tc_plan(int K, int N, int anchors, int mode, int* Nc_out, int* nchunks_out, int* stages_out, int* halo_slots_out) {
+struct TcPlan {
+  int Nc = 0, nchunks = 0, stages = 0, halo_slots = 0, wstream = 0;
+  int tile_w = TC_TILE_W, tile_h = TC_TILE_H, halo_w = 0, halo_pix = 0, halo_bytes = 0;
+  size_t smem = 0;
+};
+
+// MODE 2 spatial tile: tile_w (multiple of 4) x tile_h <= 128 pixels minimising halo pixels loaded + GEMM rows issued
+static void tc_pick_tile(int ks, int Hout, int Wout, TcPlan* pl) {
+  long long best = -1;
+  for (int tw = 4; tw <= 128; tw += 4) {
+    const int th = 128 / tw;
+    const int hp = (tw + ks - 1) * (th + ks - 1);
+    if (hp * 128 > 48 * 1024) continue;                          // keep a ring of >= 2 slots affordable
+    const long long ntile = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
+    const long long cost = ntile * (hp + 128);
+    if (best < 0 || cost < best) { best = cost; pl->tile_w = tw; pl->tile_h = th; pl->halo_w = tw + ks - 1; pl->halo_pix = hp; }
+  }
+  pl->halo_bytes = pl->halo_pix * 128;
+}
+
+// MODE 2 with weights too large to stay resident next to the halo ring: one K-slab (hi, lo) of W per A stage, from L2
+static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
+  (void)nslab;
+  const size_t fixed = (size_t)2 * (2 * TC_SLAB_BYTES + 2 * Npad * 128) + TC_AUX_BYTES + dw_bytes + 1024;
+  if (fixed + 2 * (size_t)pl->halo_bytes > (size_t)TC_SMEM_BUDGET) return false;
+  pl->Nc = Npad; pl->nchunks = 1; pl->wstream = 1; pl->stages = 2;
+  pl->halo_slots = 2;
+  while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
+  pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
+  return true;
+}
+
+static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
   const int Npad = (N + 15) / 16 * 16;
+  if (mode == 2) {
+    if (dw_ks != 3 && dw_ks != 5) return false;
+    tc_pick_tile(dw_ks, Hout, Wout, pl);
+  }
+  const size_t dw_bytes = mode == 2 ? (size_t)(dw_ks * dw_ks + 1) * nslab * 32 * 4 : 0;
   for (int nch = 1; nch <= 4; ++nch) {
     int Nc = ((Npad / 16 + nch - 1) / nch) * 16;
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
     const size_t wbytes = (size_t)2 * nslab * Nc * 128;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
     size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
-    int halo_slots = 0;
+    pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 0; pl->halo_slots = 0;
     if (mode == 3) {                             // stem-output halo + input patch, 2 A stages
       fixed += (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES + 2 * 2 * TC_SLAB_BYTES;
       if (fixed > (size_t)TC_SMEM_BUDGET) continue;
-      *Nc_out = Nc; *nchunks_out = nch; *stages_out = 2; *halo_slots_out = 0;
+      pl->stages = 2; pl->smem = fixed;
       return true;
     }
-    if (mode == 2) {                             // halo ring (2..3 slots) + depthwise weights, 2 A stages
-      fixed += (size_t)9 * nslab * 32 * 4 + 2 * 2 * TC_SLAB_BYTES;
-      if (fixed + 2 * TC_HALO_BYTES > (size_t)TC_SMEM_BUDGET) continue;
-      halo_slots = (fixed + 3 * TC_HALO_BYTES <= (size_t)TC_SMEM_BUDGET) ? 3 : 2;
-      *Nc_out = Nc; *nchunks_out = nch; *stages_out = 2; *halo_slots_out = halo_slots;
+    if (mode == 2) {                             // halo ring (2..4 slots) + depthwise weights, 2 A stages
+      fixed += dw_bytes + 2 * 2 * TC_SLAB_BYTES;
+      if (fixed + 2 * pl->halo_bytes > (size_t)TC_SMEM_BUDGET) continue;
+      // splitting N over CTAs repeats the depthwise stage in every chunk: when the whole N fits one CTA's TMEM, streaming
+      // the weight slabs (below) is cheaper than chunking
+      if (nch > 1 && Npad <= 128 && (N & 3) == 0 && tc_plan_stream(nslab, Npad, dw_bytes, pl)) return true;
+      pl->halo_slots = 2;
+      while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
+      pl->stages = 2; pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
       return true;
     }
     if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
     int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    *Nc_out = Nc; *nchunks_out = nch; *stages_out = stages; *halo_slots_out = 0;
+    pl->stages = stages; pl->smem = fixed + (size_t)stages * 2 * TC_SLAB_BYTES;
     return true;
   }
+  if (mode == 2 && Npad <= 128 && (N & 3) == 0) return tc_plan_stream(nslab, Npad, dw_bytes, pl);
   return false;
+}
+
+bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout) {
+  TcPlan pl;
+  return tc_plan(K, N, anchors, mode, dw_ks, Hout, Wout, &pl);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 4-D map over an NHWC fp32 activation: box = 32 channels x halo_w x halo_h x 1 image, dense [hy][hx][32] in shared memory;
+// coordinates outside the tensor (negative / past the edge / channels past C) read as zero.
+static int make_halo_tmap(CUtensorMap* tm, const float* in, int B, int H, int W, int C, int halo_w, int halo_h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  YL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4};
+  const cuuint32_t box[4] = {32, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the halo tile");
+  return 0;
 }
 
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st) {
@@ -872,7 +1027,10 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;      // mode 3: c.Cin = 32 stem channels, KS = 3 -> 288
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
-  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, &p.Nc, &p.nchunks, &p.stages, &p.halo_slots), "shape does not fit the tcgen05 conv kernel");
+  TcPlan pl;
+  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl), "shape does not fit the tcgen05 conv kernel");
+  p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
+  p.tile_w = pl.tile_w; p.tile_h = pl.tile_h; p.halo_w = pl.halo_w; p.halo_pix = pl.halo_pix; p.halo_bytes = pl.halo_bytes;
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE((c.Cin & 3) == 0, "tcgen05 conv needs Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
@@ -883,9 +1041,10 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
     p.Ws = (c.Win + 2 - 3) / 2 + 1;
   }
   if (mode >= 2) {
-    YL_REQUIRE(!c.res && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0, "fused DWConvBlock epilogue takes no residual/upsample/head layout");
-    p.tiles_x = (c.Wout + TC_TILE_W - 1) / TC_TILE_W;
-    p.tiles_y = (c.Hout + TC_TILE_H - 1) / TC_TILE_H;
+    YL_REQUIRE(!c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (mode == 2 || !c.res), "fused depthwise/stem epilogue takes no upsample/head layout");
+    YL_REQUIRE(mode == 3 || (c.stride == 1 && c.Hin == c.Hout && c.Win == c.Wout && c.w2), "fused depthwise -> pointwise keeps the spatial size");
+    p.tiles_x = (c.Wout + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (c.Hout + p.tile_h - 1) / p.tile_h;
     p.num_tiles = c.B * p.tiles_x * p.tiles_y;
   }
   YL_REQUIRE(p.M * c.Cout < (1ll << 31), "output too large for 32-bit element offsets");
@@ -895,26 +1054,31 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   while (cols < 4 * p.Nc) cols <<= 1;
   if (mode == 3) { YL_REQUIRE(p.Nc <= 32, "fused stem kernel: N chunk <= 32"); cols = 128; }
   p.tmem_cols = cols;
-  const size_t smem = (size_t)2 * p.nslab * p.Nc * 128 + (size_t)p.stages * 2 * TC_SLAB_BYTES + TC_AUX_BYTES +
-                      (p.dense_epi ? (size_t)4 * 32 * p.Nc * 4 : 0) +
-                      (mode == 2 ? (size_t)p.halo_slots * TC_HALO_BYTES + (size_t)9 * p.nslab * 32 * 4 : 0) +
-                      (mode == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0) + 1024;
+  const size_t smem = pl.smem;
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int gx = sm_count / p.nchunks;
   if (gx < 1) gx = 1;
   if (gx > p.num_tiles) gx = p.num_tiles;
   dim3 grid(gx, p.nchunks);
-  if (mode == 0) tc_conv_kernel<0><<<grid, TC_THREADS, smem, st>>>(p);
-  else if (mode == 1) tc_conv_kernel<1><<<grid, TC_THREADS, smem, st>>>(p);
-  else if (mode == 2) tc_conv_kernel<2><<<grid, TC_THREADS, smem, st>>>(p);
-  else tc_conv_kernel<3><<<grid, TC_THREADS, smem, st>>>(p);
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (mode == 2) {
+    YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && p.tile_h + c.KS - 1 <= 256, "halo tile does not fit a TMA box");
+    if (int rc = make_halo_tmap(&tmap, c.in, c.B, c.Hin, c.Win, c.Cin, pl.halo_w, p.tile_h + c.KS - 1)) return rc;
+  }
+  if (mode == 0) tc_conv_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+  else if (mode == 1) tc_conv_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+  else if (mode == 2 && c.KS == 3) tc_conv_kernel<2, 3><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+  else if (mode == 2) tc_conv_kernel<2, 5><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+  else tc_conv_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
