@@ -49,7 +49,6 @@ struct Stem2Params {
   float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
   int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
   int tiles_x, tiles_y, num_tiles;
-  int pass_mask;                       // debug: bit ps enables pass ps of both GEMMs (default 63)
 };
 
 namespace s2 {
@@ -239,8 +238,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
     if (lane == 0) {
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N2 >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t a1_u = smem_u32(a1), wst_u = smem_u32(wst), w2_u = smem_u32(w2s), pl_u = smem_u32(planes);
-      const uint32_t w2_split = 9u * (uint32_t)p.N2 * 64u, w2_tap = (uint32_t)p.N2 * 64u;
+      // Descriptor bases: every operand address below is base + a compile-time (or per-launch) multiple of 16 B, and all
+      // of shared memory fits the 14-bit start-address field, so each MMA's descriptors cost one 64-bit add.
+      const uint64_t dA1 = desc64(smem_u32(a1), 512), dWs = desc64(smem_u32(wst), 512), dW2 = desc64(smem_u32(w2s), 512);
+      const uint64_t dP[2] = {desc64(smem_u32(planes), 9u * 64u), desc64(smem_u32(planes), 8u * 64u)};   // SBO = plane pitch
+      const uint32_t w2_split16 = 9u * (uint32_t)p.N2 * 4u, w2_tap16 = (uint32_t)p.N2 * 4u;            // in 16 B units
       uint32_t n = 0;
       // (A split, W split) of the six passes; pass 0 goes to the main accumulator, the rest to the correction accumulator
       auto gemm1 = [&](uint32_t it) {
@@ -250,18 +252,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
           mbar_wait(smem_u32(&a1_full[stage]), (n >> 1) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t dm = tmem_base + 64u * (uint32_t)j, dc = dm + 32u;
-          const uint32_t ab = a1_u + stage * S2_A1_STAGE;
-          uint32_t first_c = 0;
+          const uint64_t da0 = dA1 + (uint64_t)(stage * (S2_A1_STAGE >> 4));
 #pragma unroll
           for (int ps = 0; ps < 6; ++ps) {
             const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);      // A split: 0,0,1,1,0,2
             const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);      // W split: 0,1,0,1,2,0
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = desc64(ab + sa * S2_A1_SPLIT + ks * 32, 512), db = desc64(wst_u + sw * 2048 + ks * 32, 512);
-              if (!((p.pass_mask >> ps) & 1)) continue;
+              const uint64_t da = da0 + (uint64_t)((sa * S2_A1_SPLIT + ks * 32) >> 4), db = dWs + (uint64_t)((sw * 2048 + ks * 32) >> 4);
               if (ps == 0) mma_bf16(dm, da, db, idesc1, ks > 0);
-              else { mma_bf16(dc, da, db, idesc1, first_c); first_c = 1; }
+              else mma_bf16(dc, da, db, idesc1, (ps > 1 || ks > 0) ? 1u : 0u);
             }
           }
           mma_commit(smem_u32(&a1_empty[stage]));
@@ -274,23 +274,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
         mbar_wait(smem_u32(halo_full), it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t dm = tmem_base + ACC2_COL + 64u * b, dc = dm + 32u;
-        uint32_t first_m = 0, first_c = 0;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3, px = kx & 1;
-          const uint32_t pw = px ? 8u : 9u;
-          const uint32_t aoff = ((uint32_t)s2_plane_off(ky & 1, px) + (uint32_t)(ky >> 1) * pw + (uint32_t)(kx >> 1)) * 64u;
-          const uint32_t sbo = pw * 64u;
+          const int pw = px ? 8 : 9;
+          const int aoff = (s2_plane_off(ky & 1, px) + (ky >> 1) * pw + (kx >> 1)) * 64;
+          const uint64_t dbt = dW2 + (uint64_t)((uint32_t)tap * w2_tap16);
 #pragma unroll
           for (int ps = 0; ps < 6; ++ps) {
             const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);
             const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = desc64(pl_u + sa * S2_PLANE_BYTES + aoff + ks * 32, sbo);
-              const uint64_t db = desc64(w2_u + sw * w2_split + tap * w2_tap + ks * 32, 512);
-              if (!((p.pass_mask >> (ps + 8)) & 1)) continue;
-              if (ps == 0) { mma_bf16(dm, da, db, idesc2, first_m); first_m = 1; }
-              else { mma_bf16(dc, da, db, idesc2, first_c); first_c = 1; }
+              const uint64_t da = dP[px] + (uint64_t)((sa * S2_PLANE_BYTES + aoff + ks * 32) >> 4);
+              const uint64_t db = dbt + (uint64_t)((uint32_t)sw * w2_split16 + (uint32_t)(ks * 2));
+              if (ps == 0) mma_bf16(dm, da, db, idesc2, (tap > 0 || ks > 0) ? 1u : 0u);
+              else mma_bf16(dc, da, db, idesc2, (tap > 0 || ps > 1 || ks > 0) ? 1u : 0u);
             }
           }
         }
@@ -432,8 +431,6 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
   const long long nt = (long long)p.B * p.tiles_x * p.tiles_y;
   YL_REQUIRE(nt < (1ll << 31) && (long long)p.B * p.Ho * p.Wo * p.Cout < (1ll << 40), "too many tiles");
   p.num_tiles = (int)nt;
-  static const int mask_env = [] { const char* e = getenv("YL_S2_PASSES"); return e ? (int)strtol(e, nullptr, 0) : 0x3F3F; }();
-  p.pass_mask = mask_env;
   const size_t smem = stem2_smem_bytes(p.N2);
   static thread_local bool attr_set = false;
   if (!attr_set) {

@@ -58,6 +58,7 @@ struct TcParams {
   int halo_slots;       // MODE 2: halo ring depth
   int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
   int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
+  int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
   int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
                         // streamed from L2 into the A stage's own W slot with cp.async.bulk
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
@@ -384,6 +385,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         if (lane == 0) mbar_arrive(smem_u32(halo_empty));           // this warp no longer reads the halo
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else if (MODE == 0 && p.tma_a) {
+      // The TMA warp lands each K-slab of the A tile (raw fp32 = the hi operand) straight in the swizzled UMMA layout;
+      // every producer thread derives lo = a - trunc_tf32(a) for its own four 16 B pieces.
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = my_tiles * p.nslab;
+      uint32_t soff[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = r0 + 32 * i;
+        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < total; ++j) {
+        mbar_wait(smem_u32(&wfull_bar[stage]), phase);
+        unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+        float4 a[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(hi + soff[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float4 h, l;
+          if (p.raw_hi) {
+            l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
+            l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
+            l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
+            l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
+          } else {
+            h.x = tf32_rn(a[i].x); h.y = tf32_rn(a[i].y); h.z = tf32_rn(a[i].z); h.w = tf32_rn(a[i].w);
+            l.x = tf32_rn(a[i].x - h.x); l.y = tf32_rn(a[i].y - h.y); l.z = tf32_rn(a[i].z - h.z); l.w = tf32_rn(a[i].w - h.w);
+            *reinterpret_cast<float4*>(hi + soff[i]) = h;
+          }
+          *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
     } else if (MODE != 2) {
       // cp.async pipeline: the 16 B pieces are copied global -> shared (zero-filled outside the image / past K) straight
       // into their swizzled slot of the stage's `hi` slab, up to `depth` K-slabs ahead of the one being converted, so
@@ -569,6 +609,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         if (++c_s == p.nslab) c_s = 0;
       }
     }
+  } else if (MODE == 0 && warp == TC_TMA_WARP) {
+    // =============================== TMA issuer (MODE 0) ===============================
+    if (p.tma_a && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        for (int s = 0; s < p.nslab; ++s) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage are done
+          const uint32_t bar = smem_u32(&wfull_bar[stage]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TC_SLAB_BYTES) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                       ::"r"(smem_u32(a_ring) + (uint32_t)stage * 2u * TC_SLAB_BYTES), "l"(&tmap), "r"(s * 32), "r"(tile * TC_BM), "r"(bar)
+                       : "memory");
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
   } else if (MODE == 2 && warp == TC_TMA_WARP) {
     // =============================== TMA issuer (MODE 2) ===============================
     if (lane == 0) {
@@ -1017,6 +1075,21 @@ static int make_halo_tmap(CUtensorMap* tm, const float* in, int B, int H, int W,
   return 0;
 }
 
+// 2-D map over a pointwise conv's A matrix [M][C] fp32: box = 32 k x 128 rows, SWIZZLE_128B = the K-major UMMA layout
+static int make_a_tmap(CUtensorMap* tm, const float* in, long long M, int C) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  YL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)M};
+  const cuuint64_t strides[1] = {(cuuint64_t)C * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(in), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed for the A tile");
+  return 0;
+}
+
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st) {
   TcParams p{};
   p.c = c;
@@ -1070,6 +1143,11 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   dim3 grid(gx, p.nchunks);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
+  static const int tma_env = [] { const char* e = getenv("YL_TC_TMA"); return e ? atoi(e) : 1; }();
+  if (mode == 0 && tma_env && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0) {
+    if (int rc = make_a_tmap(&tmap, c.in, p.M, c.Cin)) return rc;
+    p.tma_a = 1;
+  }
   if (mode == 2) {
     YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && p.tile_h + c.KS - 1 <= 256, "halo tile does not fit a TMA box");
     if (int rc = make_halo_tmap(&tmap, c.in, c.B, c.Hin, c.Win, c.Cin, pl.halo_w, p.tile_h + c.KS - 1)) return rc;
