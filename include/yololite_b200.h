@@ -68,7 +68,7 @@ typedef struct yl_op {
   int64_t wt_off;    /* float offset of the tcgen05 weight image [2 (hi,lo)][ceil(K/32)][ceil16(cout)][32], pre-split
                         into TF32 hi/lo and pre-swizzled (SWIZZLE_128B, K-major), or -1 */
   int64_t w3_off;    /* YL_OP_STEM2: float offset of the bf16-triple weight image of the fused stem kernel
-                        ([3 splits][9 taps][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
+                        ([9 taps][3 splits][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
                         row 64 B, SWIZZLE_64B K-major, two bf16 per float slot), or -1 (older tf32 kernel) */
   int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1 */
   int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv */

@@ -3,15 +3,17 @@
 // YoloLite_custom_training.ipynb:392-410.  The 13 MB/image stem activation never reaches HBM.
 //
 // Operands are error-compensated bf16 triples: every fp32 value x = x1 + x2 + x3 (x1 = bf16(x), x2 = bf16(x - x1),
-// x3 = bf16(x - x1 - x2)), D = A1*W1 (main accumulator) + A1*W2 + A2*W1 + A2*W2 + A1*W3 + A3*W1 (correction accumulator),
-// dropped terms are 2^-24 relative.  uint8 images are exact in ONE bf16, so the image path runs 3 passes instead of 6.
+// x3 = bf16(x - x1 - x2)), D = A1*W1 (main accumulator) + A1*W2 + A2*W1 + A2*W2 + A1*W3 + A3*W1 (correction accumulators),
+// dropped terms are 2^-24 relative.  The three weight splits sit side by side along N ([W1 | W2 | W3]), so the six
+// products take THREE instructions per k-step -- A1 x [W1|W2|W3], A2 x [W1|W2], A3 x [W1] -- into three adjacent
+// accumulator blocks [main | corr | corr]: the kernel is bound by shared-memory operand reads, and this halves them.
 //
 // Per 16x8 tile of conv2 output pixels (one persistent CTA per SM, 17 warps, warp-specialised):
 //   warps 8-15  producers: cp.async the 3 x 67 x 36 fp32 input patch (NCHW) into shared memory, build the stem's im2col
 //               operand (K = 27 taps + a constant-1 column that carries the folded BN bias, padded to 32) for five
 //               128-row tiles covering the 33 x 17 halo of stem output pixels;
-//   warp  16    one thread issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128, N = 32, K = 32) into five TMEM
-//               accumulator pairs, GEMM2 = conv2 as nine per-tap GEMMs (M = 128, N = 16, K = 32);
+//   warp  16    one thread issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128, N = 96|64|32, K = 32) into a ring of
+//               three TMEM accumulator triples, GEMM2 = conv2 as nine per-tap GEMMs (M = 128, N = 3|2|1 x N2, K = 32);
 //   warps 0-7   epilogue: TMEM -> ReLU -> bf16 triple -> shared-memory halo stored as four parity planes
 //               (row parity x column parity); then conv2's accumulator -> bias + ReLU -> NHWC global stores.
 // GEMM2 has NO im2col copy: for tap (ky, kx) the A operand of the 16x8 tile is the parity plane (ky&1, kx&1) shifted
@@ -39,12 +41,14 @@ constexpr int S2_PLANE_BYTES = (S2_HPIX * 64 + 511) / 512 * 512;   // one bf16 s
 constexpr int S2_A1_SPLIT = 128 * 64, S2_A1_STAGE = 3 * S2_A1_SPLIT;
 constexpr int S2_PATCH_BYTES = 3 * S2_PR * S2_PP * 4;      // 28944
 constexpr int S2_WST_BYTES = 3 * 32 * 64;                  // stem weights, three splits
+constexpr int S2_ACC1_RING = 3;                            // stem accumulator ring: 3 x [main 32 | corr 32 | corr 32] TMEM columns
+constexpr uint32_t S2_ACC1_COLS = 96, S2_ACC2_COL = S2_ACC1_RING * S2_ACC1_COLS, S2_ACC2_COLS = 96;   // conv2: 2 x 3*N2 (<= 96)
 // parity planes (py, px): pixel offsets inside one split, pitch 9 (px = 0) or 8 (px = 1)
 __host__ __device__ constexpr int s2_plane_off(int py, int px) { return py ? (px ? 433 : 289) : (px ? 153 : 0); }
 
 struct Stem2Params {
   const float* __restrict__ in;        // [B,3,H,W] fp32 NCHW
-  const float* __restrict__ wimg;      // bf16 image: [3 splits][9 taps][N2][32] SW64 | [3 splits][32][32] SW64
+  const float* __restrict__ wimg;      // bf16 image: [9 taps][3 splits][N2][32] SW64 | [3 splits][32][32] SW64
   const float* __restrict__ bias2;     // [Cout]
   float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
   int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
@@ -132,8 +136,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + S2_PATCH_BYTES);
   uint64_t* a1_full = bars;            // [2]  producers (8 warps) -> MMA
   uint64_t* a1_empty = bars + 2;       // [2]  MMA commit -> producers
-  uint64_t* acc1_full = bars + 4;      // [5]  MMA commit -> epilogue
-  uint64_t* acc1_free = bars + 9;      // [5]  epilogue (8 warps) -> MMA
+  uint64_t* acc1_full = bars + 4;      // [3]  MMA commit -> epilogue   (ring over the stem sub-tiles)
+  uint64_t* acc1_free = bars + 9;      // [3]  epilogue (8 warps) -> MMA
   uint64_t* halo_full = bars + 14;     //      epilogue (8 warps) -> MMA
   uint64_t* halo_free = bars + 15;     //      MMA commit -> epilogue
   uint64_t* acc2_full = bars + 16;     // [2]  MMA commit -> epilogue
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS); mbar_init(smem_u32(&a1_empty[s]), 1); }
-    for (int j = 0; j < S2_MT; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
+    for (int j = 0; j < S2_ACC1_RING; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
     mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
     mbar_init(smem_u32(halo_free), 1);
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc2_full[b]), 1); mbar_init(smem_u32(&acc2_free[b]), S2_EPI_WARPS); }
@@ -164,8 +168,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
   const int per_img = p.tiles_x * p.tiles_y;
-  // TMEM columns: stem tile j: main 64j, corr 64j + 32; conv2 buffer b: main 320 + 64b, corr 352 + 64b
-  constexpr uint32_t ACC2_COL = 64 * S2_MT;
+  // TMEM columns: stem ring slot r: [96r, 96r + 96) = main | corr | corr (32 each); conv2 buffer b: 288 + 96b + {0, N2, 2*N2}
+  constexpr uint32_t ACC2_COL = S2_ACC2_COL;
 
   if (warp >= S2_EPI_WARPS && warp < S2_EPI_WARPS + S2_PROD_WARPS) {
     // =============================== producers ===============================
@@ -236,36 +240,33 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
   } else if (warp == S2_MMA_WARP) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
-      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.N2 >> 3) << 17) | ((128u >> 4) << 24);
+      auto idesc = [](uint32_t N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24); };
+      const uint32_t i1a = idesc(96), i1b = idesc(64), i1c = idesc(32);
+      const uint32_t N2 = (uint32_t)p.N2, i2a = idesc(3 * N2), i2b = idesc(2 * N2), i2c = idesc(N2);
       // Descriptor bases: every operand address below is base + a compile-time (or per-launch) multiple of 16 B, and all
       // of shared memory fits the 14-bit start-address field, so each MMA's descriptors cost one 64-bit add.
       const uint64_t dA1 = desc64(smem_u32(a1), 512), dWs = desc64(smem_u32(wst), 512), dW2 = desc64(smem_u32(w2s), 512);
       const uint64_t dP[2] = {desc64(smem_u32(planes), 9u * 64u), desc64(smem_u32(planes), 8u * 64u)};   // SBO = plane pitch
-      const uint32_t w2_split16 = 9u * (uint32_t)p.N2 * 4u, w2_tap16 = (uint32_t)p.N2 * 4u;            // in 16 B units
-      uint32_t n = 0;
-      // (A split, W split) of the six passes; pass 0 goes to the main accumulator, the rest to the correction accumulator
-      auto gemm1 = [&](uint32_t it) {
-        for (int j = 0; j < S2_MT; ++j, ++n) {
+      const uint32_t w2_tap16 = 3u * N2 * 4u;                                                            // in 16 B units
+      uint32_t n = 0, slot = 0, sphase = 0;
+      auto gemm1 = [&](int j0, int j1) {
+        for (int j = j0; j < j1; ++j, ++n) {
           const uint32_t stage = n & 1u;
-          mbar_wait(smem_u32(&acc1_free[j]), (it & 1u) ^ 1u);
+          mbar_wait(smem_u32(&acc1_free[slot]), sphase ^ 1u);
           mbar_wait(smem_u32(&a1_full[stage]), (n >> 1) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t dm = tmem_base + 64u * (uint32_t)j, dc = dm + 32u;
+          const uint32_t d0 = tmem_base + S2_ACC1_COLS * slot;
           const uint64_t da0 = dA1 + (uint64_t)(stage * (S2_A1_STAGE >> 4));
 #pragma unroll
-          for (int ps = 0; ps < 6; ++ps) {
-            const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);      // A split: 0,0,1,1,0,2
-            const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);      // W split: 0,1,0,1,2,0
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = da0 + (uint64_t)((sa * S2_A1_SPLIT + ks * 32) >> 4), db = dWs + (uint64_t)((sw * 2048 + ks * 32) >> 4);
-              if (ps == 0) mma_bf16(dm, da, db, idesc1, ks > 0);
-              else mma_bf16(dc, da, db, idesc1, (ps > 1 || ks > 0) ? 1u : 0u);
-            }
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t db = dWs + (uint64_t)((ks * 32) >> 4);
+            mma_bf16(d0, da0 + (uint64_t)((0 * S2_A1_SPLIT + ks * 32) >> 4), db, i1a, ks > 0);        // A1 x [W1|W2|W3]
+            mma_bf16(d0 + 32u, da0 + (uint64_t)((1 * S2_A1_SPLIT + ks * 32) >> 4), db, i1b, 1u);      // A2 x [W1|W2]
+            mma_bf16(d0 + 64u, da0 + (uint64_t)((2 * S2_A1_SPLIT + ks * 32) >> 4), db, i1c, 1u);      // A3 x [W1]
           }
           mma_commit(smem_u32(&a1_empty[stage]));
-          mma_commit(smem_u32(&acc1_full[j]));
+          mma_commit(smem_u32(&acc1_full[slot]));
+          if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
         }
       };
       auto gemm2 = [&](uint32_t it) {
@@ -273,24 +274,19 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
         mbar_wait(smem_u32(&acc2_free[b]), ((it >> 1) & 1u) ^ 1u);
         mbar_wait(smem_u32(halo_full), it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t dm = tmem_base + ACC2_COL + 64u * b, dc = dm + 32u;
+        const uint32_t d0 = tmem_base + ACC2_COL + S2_ACC2_COLS * b;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
           const int ky = tap / 3, kx = tap - ky * 3, px = kx & 1;
           const int pw = px ? 8 : 9;
           const int aoff = (s2_plane_off(ky & 1, px) + (ky >> 1) * pw + (kx >> 1)) * 64;
-          const uint64_t dbt = dW2 + (uint64_t)((uint32_t)tap * w2_tap16);
 #pragma unroll
-          for (int ps = 0; ps < 6; ++ps) {
-            const int sa = (ps == 2 || ps == 3) ? 1 : (ps == 5 ? 2 : 0);
-            const int sw = (ps == 1 || ps == 3) ? 1 : (ps == 4 ? 2 : 0);
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks) {
-              const uint64_t da = dP[px] + (uint64_t)((sa * S2_PLANE_BYTES + aoff + ks * 32) >> 4);
-              const uint64_t db = dbt + (uint64_t)((uint32_t)sw * w2_split16 + (uint32_t)(ks * 2));
-              if (ps == 0) mma_bf16(dm, da, db, idesc2, (tap > 0 || ks > 0) ? 1u : 0u);
-              else mma_bf16(dc, da, db, idesc2, (tap > 0 || ps > 1 || ks > 0) ? 1u : 0u);
-            }
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint64_t db = dW2 + (uint64_t)((uint32_t)tap * w2_tap16 + (uint32_t)(ks * 2));
+            const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
+            mma_bf16(d0, dP[px] + (uint64_t)((0 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2a, acc);
+            mma_bf16(d0 + N2, dP[px] + (uint64_t)((1 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2b, 1u);
+            mma_bf16(d0 + 2u * N2, dP[px] + (uint64_t)((2 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2c, 1u);
           }
         }
         mma_commit(smem_u32(halo_free));
@@ -298,9 +294,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
       };
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        if (it == 0) gemm1(0);
-        if (tile + (int)gridDim.x < tiles) gemm1(it + 1);       // next tile's stem GEMMs, paced by acc1_free
+        // The accumulator ring holds 3 of a tile's 5 stem sub-tiles, and the epilogue cannot drain the next tile's second
+        // sub-tile before conv2 of this tile has released the halo: issue three of the next tile's stem GEMMs, then this
+        // tile's conv2, then the remaining two.
+        const bool more = tile + (int)gridDim.x < tiles;
+        if (it == 0) gemm1(0, S2_MT);
+        if (more) gemm1(0, S2_ACC1_RING);
         gemm2(it);
+        if (more) gemm1(S2_ACC1_RING, S2_MT);
       }
     }
     __syncwarp();
@@ -319,11 +320,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
       const int y = ty * S2_TH + (r >> 3), x = tx * S2_TW + (r & 7);
       const int ncol = p.N2 >> 1;                               // columns per half: 8 (N2 = 16) or 16 (N2 = 32)
       for (int c0 = 0; c0 < ncol; c0 += 8) {
-        uint32_t m[8], k[8];
-        const uint32_t col = ACC2_COL + 64u * b + (uint32_t)(half * ncol + c0);
+        uint32_t m[8], k[8], k2[8];
+        const uint32_t col = ACC2_COL + S2_ACC2_COLS * b + (uint32_t)(half * ncol + c0);
         tmem_ld8(lane_addr + col, m);
-        tmem_ld8(lane_addr + col + 32u, k);
+        tmem_ld8(lane_addr + col + (uint32_t)p.N2, k);
+        tmem_ld8(lane_addr + col + 2u * (uint32_t)p.N2, k2);
         tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 8; ++g) k[g] = __float_as_uint(__uint_as_float(k[g]) + __uint_as_float(k2[g]));
         const int nn = half * ncol + c0;
         if (y < p.Ho && x < p.Wo) {
           float* dst = p.out + (((size_t)bi * p.Ho + y) * p.Wo + x) * p.Cout + nn;
@@ -345,22 +349,33 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&acc2_free[b]));
     };
-    uint32_t it = 0;
+    uint32_t it = 0, slot = 0, sphase = 0;
     int prev_tile = -1;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int rem = tile % per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int sy0 = 2 * S2_TH * ty - 1, sx0 = 2 * S2_TW * tx - 1;
       for (int j = 0; j < S2_MT; ++j) {
-        mbar_wait(smem_u32(&acc1_full[j]), it & 1u);
+        mbar_wait(smem_u32(&acc1_full[slot]), sphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint32_t m[16], k[16];
-        tmem_ld16(lane_addr + 64u * (uint32_t)j + 16u * (uint32_t)half, m);
-        tmem_ld16(lane_addr + 64u * (uint32_t)j + 32u + 16u * (uint32_t)half, k);
-        tmem_ld_wait();
+        float v[16];                                          // main + corr + corr of this thread's 16 channels
+        {
+          const uint32_t ta = lane_addr + S2_ACC1_COLS * slot + 16u * (uint32_t)half;
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint32_t m[8], k[8], k2[8];
+            tmem_ld8(ta + 8u * h8, m);
+            tmem_ld8(ta + 32u + 8u * h8, k);
+            tmem_ld8(ta + 64u + 8u * h8, k2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[8 * h8 + c] = __uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c]));
+          }
+        }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&acc1_free[j]));
+        if (lane == 0) mbar_arrive(smem_u32(&acc1_free[slot]));
+        if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
         if (j == 0) mbar_wait(smem_u32(halo_free), (it & 1u) ^ 1u);   // conv2 of the previous tile has read the halo
         const int q = j * 128 + q4 * 32 + lane;
         if (q < S2_HPIX) {
@@ -370,8 +385,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
           uint32_t o1[8], o2[8], o3[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
-            float a = fmaxf(__uint_as_float(m[2 * c]) + __uint_as_float(k[2 * c]), 0.f);          // bias rides in the GEMM (k = 27)
-            float b = fmaxf(__uint_as_float(m[2 * c + 1]) + __uint_as_float(k[2 * c + 1]), 0.f);
+            float a = fmaxf(v[2 * c], 0.f);          // bias rides in the GEMM (k = 27)
+            float b = fmaxf(v[2 * c + 1], 0.f);
             if (!in_img) { a = 0.f; b = 0.f; }
             split3(a, b, o1[c], o2[c], o3[c]);
           }

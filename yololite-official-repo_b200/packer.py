@@ -206,7 +206,8 @@ def _sw64_rows(m: np.ndarray) -> np.ndarray:
 
 def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
     """Weight image of the fused stem kernel as float32 words (two bf16 per word, bits preserved):
-    [3 splits][9 taps][ceil16(n_out)][32 ch] conv2 weights, then [3 splits][32 stem ch][32 k] stem weights where
+    [9 taps][3 splits][ceil16(n_out)][32 ch] conv2 weights (the three splits of a tap are adjacent row blocks, so one
+    MMA can take [W1|W2|W3], [W1|W2] or [W1] as its B operand), then [3 splits][32 stem ch][32 k] stem weights where
     k = (ky*3 + kx)*3 + ci for k < 27, k = 27 is the folded BN bias (multiplied by a constant-1 column), k > 27 zero.
     w2m: [288][>= n_out] with k = (ky*3 + kx)*32 + ci; ws: [27][32]; b0: [32]."""
     n2 = (n_out + 15) // 16 * 16
@@ -216,8 +217,10 @@ def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> 
     st[:, :27] = np.asarray(ws, np.float64).T.astype(np.float32)
     st[:, 27] = np.asarray(b0, np.float64).astype(np.float32)
     parts = []
-    for sp in bf16_split3(w2):
-        parts.append(np.concatenate([_sw64_rows(sp[t]) for t in range(9)]).reshape(-1))
+    sp2 = bf16_split3(w2)
+    for t in range(9):
+        for sp in sp2:
+            parts.append(_sw64_rows(sp[t]).reshape(-1))
     for sp in bf16_split3(st):
         parts.append(_sw64_rows(sp).reshape(-1))
     return np.concatenate(parts).astype(np.uint16).view(np.float32)
