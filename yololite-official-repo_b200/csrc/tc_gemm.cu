@@ -58,6 +58,8 @@ struct TcParams {
   int halo_slots;       // MODE 2: halo ring depth
   int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
   int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
+  int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
+  int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
   int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
   int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
                         // streamed from L2 into the A stage's own W slot with cp.async.bulk
@@ -219,7 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(smem_u32(&full_bar[s]), TC_PROD_WARPS); mbar_init(smem_u32(&empty_bar[s]), 1); mbar_init(smem_u32(&wfull_bar[s]), 1);
+      mbar_init(smem_u32(&full_bar[s]), p.prod_warps); mbar_init(smem_u32(&empty_bar[s]), 1); mbar_init(smem_u32(&wfull_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
     mbar_init(smem_u32(halo_full), 4);
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
 
-  if (warp < TC_PROD_WARPS) {
+  if (warp < p.prod_warps) {
     // =============================== producers ===============================
     // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
@@ -387,37 +389,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     } else if (MODE == 0 && p.tma_a) {
       // The TMA warp lands each K-slab of the A tile (raw fp32 = the hi operand) straight in the swizzled UMMA layout;
-      // every producer thread derives lo = a - trunc_tf32(a) for its own four 16 B pieces.
+      // every producer thread derives lo = a - trunc_tf32(a) for its own 16 B pieces (4 with 8 producer warps, 8 with 4).
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
-      uint32_t soff[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = r0 + 32 * i;
-        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-      }
+      const int rstep = p.prod_warps * 4;                         // rows covered by one pass of the producer threads
+      const int npass = TC_BM / (4 * rstep);                     // passes of 4 pieces per thread: 1 or 2
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < total; ++j) {
         mbar_wait(smem_u32(&wfull_bar[stage]), phase);
         unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-        float4 a[4];
+        for (int ps = 0; ps < npass; ++ps) {
+          uint32_t soff[4];
+          float4 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(hi + soff[i]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4 h, l;
-          if (p.raw_hi) {
-            l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
-            l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
-            l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
-            l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
-          } else {
-            h.x = tf32_rn(a[i].x); h.y = tf32_rn(a[i].y); h.z = tf32_rn(a[i].z); h.w = tf32_rn(a[i].w);
-            l.x = tf32_rn(a[i].x - h.x); l.y = tf32_rn(a[i].y - h.y); l.z = tf32_rn(a[i].z - h.z); l.w = tf32_rn(a[i].w - h.w);
-            *reinterpret_cast<float4*>(hi + soff[i]) = h;
+          for (int i = 0; i < 4; ++i) {
+            const int row = r0 + rstep * (4 * ps + i);
+            soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+            a[i] = *reinterpret_cast<const float4*>(hi + soff[i]);
           }
-          *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 h, l;
+            if (p.raw_hi) {
+              l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
+              l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
+              l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
+              l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
+            } else {
+              h.x = tf32_rn(a[i].x); h.y = tf32_rn(a[i].y); h.z = tf32_rn(a[i].z); h.w = tf32_rn(a[i].w);
+              l.x = tf32_rn(a[i].x - h.x); l.y = tf32_rn(a[i].y - h.y); l.z = tf32_rn(a[i].z - h.z); l.w = tf32_rn(a[i].w - h.w);
+              *reinterpret_cast<float4*>(hi + soff[i]) = h;
+            }
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+          }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -744,19 +749,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // =============================== epilogue ===============================
     // TMEM -> registers (lane = row) -> padded smem transpose -> coalesced 16 B global accesses (lane = 4 columns,
     // 8 lanes per 128 B row segment): bias, residual and the upsampled coarser level are read with the same mapping.
-    const int q = warp - TC_EPI_WARP0;                        // TMEM lane quarter == warp index % 4
+    // With p.epi2 (MODE 0 + TMA) there are two groups of four warps: group 0 = warps 8-11 drains TMEM accumulator 0 (this
+    // CTA's even tiles), group 1 = warps 4-7 drains accumulator 1 (odd tiles), so two tiles' epilogues overlap.
+    const int q = warp & 3;                                   // TMEM lane quarter == warp index % 4
+    const int grp = warp >= TC_EPI_WARP0 ? 0 : 1;
     const int N = c.Cout;
     const int D = c.anchors > 0 ? N / c.anchors : N;
-    float* stg = epi_stage + q * (32 * TC_EPI_PITCH);
+    float* stg = epi_stage + (grp * 4 + q) * (32 * TC_EPI_PITCH);
     const bool vec = (N & 3) == 0 && c.anchors <= 1;
     // dense staging: N not a multiple of 4 (head outputs, 5+C channels), single chunk, plain [M][N] output
     const bool dense = p.dense_epi != 0;
     float* dstg = epi_stage + 4 * 32 * TC_EPI_PITCH + q * (32 * p.Nc);
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
-    int acc = 0;
+    int acc = p.epi2 ? grp : 0;
     uint32_t acc_phase = 0, hphase = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tile_step = p.epi2 ? 2 * (int)gridDim.x : (int)gridDim.x;
+    for (int tile = blockIdx.x + (p.epi2 ? grp * (int)gridDim.x : 0); tile < tiles; tile += tile_step) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
       const int rows_ok = MODE >= 2 ? 32 : min(32, M - mw);   // rows of this warp inside the matrix
       // element offset of the output row for each of the 8 rows this lane owns, -1 = outside
@@ -947,7 +956,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         for (int i = (tot4 << 2) + lane; i < tot; i += 32) dst[i] = dstg[i];
         __syncwarp();
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (p.epi2) acc_phase ^= 1;                              // this group owns one accumulator
+      else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -966,7 +976,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 static bool tc_dense_epi(int N, int anchors, int Nc, int nchunks) { return (N & 3) != 0 && anchors <= 1 && nchunks == 1 && Nc <= 128; }
 
 struct TcPlan {
-  int Nc = 0, nchunks = 0, stages = 0, halo_slots = 0, wstream = 0;
+  int Nc = 0, nchunks = 0, stages = 0, halo_slots = 0, wstream = 0, epi2 = 0;
   int tile_w = TC_TILE_W, tile_h = TC_TILE_H, halo_w = 0, halo_pix = 0, halo_bytes = 0;
   size_t smem = 0;
 };
@@ -997,7 +1007,7 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   return true;
 }
 
-static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl) {
+static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl, bool want_epi2 = false) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
   const int Npad = (N + 15) / 16 * 16;
@@ -1031,6 +1041,14 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
       return true;
     }
     if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
+    // second epilogue group (MODE 0 + TMA, plain vector epilogue): four more transpose staging buffers, if 3 stages still fit
+    const size_t epi2_bytes = (size_t)4 * 32 * TC_EPI_PITCH * 4;
+    pl->epi2 = 0;
+    if (want_epi2 && mode == 0 && dense_bytes == 0 && (N & 3) == 0 && anchors <= 1 &&
+        fixed + epi2_bytes + 3 * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) {
+      pl->epi2 = 1;
+      fixed += epi2_bytes;
+    }
     int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
     pl->stages = stages; pl->smem = fixed + (size_t)stages * 2 * TC_SLAB_BYTES;
@@ -1101,7 +1119,13 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
   TcPlan pl;
-  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl), "shape does not fit the tcgen05 conv kernel");
+  static const int tma_env = [] { const char* e = getenv("YL_TC_TMA"); return e ? atoi(e) : 1; }();
+  static const int epi2_env = [] { const char* e = getenv("YL_TC_EPI2"); return e ? atoi(e) : 1; }();
+  const bool tma_a = mode == 0 && tma_env && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0;
+  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl, tma_a && epi2_env),
+             "shape does not fit the tcgen05 conv kernel");
+  p.epi2 = pl.epi2;
+  p.prod_warps = pl.epi2 ? 4 : TC_PROD_WARPS;
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
   p.tile_w = pl.tile_w; p.tile_h = pl.tile_h; p.halo_w = pl.halo_w; p.halo_pix = pl.halo_pix; p.halo_bytes = pl.halo_bytes;
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
@@ -1143,8 +1167,7 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   dim3 grid(gx, p.nchunks);
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  static const int tma_env = [] { const char* e = getenv("YL_TC_TMA"); return e ? atoi(e) : 1; }();
-  if (mode == 0 && tma_env && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0) {
+  if (tma_a) {
     if (int rc = make_a_tmap(&tmap, c.in, p.M, c.Cin)) return rc;
     p.tma_a = 1;
   }
