@@ -295,7 +295,7 @@ def run_b200(a):
             ho, wo = out_hw(hin, win, op["k"], op["stride"])
         if op["dst"] >= 0:
             hw[op["dst"]] = (ho, wo)
-        wbytes = 4 * (op["k"] * op["k"] * op["cin"] * op["cout"] + op["cout"] + (9 * op["cin"] if op["kind"] == 3 else 0))
+        wbytes = 4 * (op["k"] * op["k"] * op["cin"] * op["cout"] + op["cout"] + (op["k2"] * op["k2"] * op["cin"] if op["kind"] == 3 else 0))
         if op["kind"] == 2:
             wbytes = 4 * (op["k"] * op["k"] * op["cin"] + op["cout"])
         nbytes = 4 * B * (hin * win * op["cin"] + ho * wo * op["cout"]) + wbytes
@@ -307,7 +307,7 @@ def run_b200(a):
         if op["kind"] in (1, 3, 4):
             kk = op["cin"] if op["kind"] == 3 or op["k"] == 1 else op["k"] * op["k"] * (32 if op["kind"] == 4 else op["cin"])
             on_tc = (not a.no_tc) and op["wt_off"] >= 0 and (op["kind"] == 4 or (kk >= 32 and op["cout"] >= 32))
-            name = ("tc_conv_kernel<" if on_tc else "conv_gemm_kernel<") + name + ">"
+            name = ("stem2_kernel<" if op["kind"] == 4 and op["w3_off"] >= 0 else "tc_conv_kernel<" if on_tc else "conv_gemm_kernel<") + name + ">"
         per_op.append((name, i, nbytes, acc[i], op))
     cand = [(t, name, i, nb) for (name, i, nb, t, op) in per_op]
     cand.append((post_ms, "post_kernel", -1, 4 * B * N * (5 + a.nc)))
@@ -315,8 +315,19 @@ def run_b200(a):
     achieved = nb_top / (t_top / 1e3) / 1e9
     desc = name_top if i_top < 0 else (f"{name_top} op#{i_top} {per_op[i_top][4]['cin']}->{per_op[i_top][4]['cout']} "
                                        f"k{per_op[i_top][4]['k']}s{per_op[i_top][4]['stride']}")
+    # DRAM traffic of that kernel per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of
+    # the same shape, committed under profiles/; see profiles/traffic.json for the source file of each entry)
+    traffic = None
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        key = name_top.split("<")[0] + (f":{per_op[i_top][4]['cin']}->{per_op[i_top][4]['cout']}" if i_top >= 0 else "")
+        if key in tj and tj[key].get("batch") == B and tj[key].get("img") == S:
+            traffic = tj[key]["dram_bytes"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "hbm", "kernel": desc, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": t_top, "algorithmic_bytes": nb_top,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": t_top, "algorithmic_bytes": nb_top,
                 "share_of_step": t_top / (fwd_ms + post_ms)}
     compulsory = (3 * S * S + N * (5 + a.nc)) * 4
     sum_bytes = sum(nb for (_, _, nb, _, _) in per_op) + 4 * B * N * (5 + a.nc)

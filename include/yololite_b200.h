@@ -37,7 +37,7 @@ enum yl_op_kind {
   YL_OP_CONV = 1,  /* dense KxK conv as implicit GEMM, NHWC -> NHWC; K=1 is the pointwise conv; epilogue:
                       +bias, +residual buffer, +nearest-upsampled coarser buffer, act, head layout       */
   YL_OP_DW = 2,    /* depthwise KxK conv (K = 3 or 5), NHWC, +bias, act                                   */
-  YL_OP_DWPW = 3,  /* fused depthwise k2 x k2 (3 or 5, stride 1, +bias b2, act2) -> pointwise + bias + residual + act;
+  YL_OP_DWPW = 3,  /* fused depthwise k2 x k2 (3 or 5, stride stride2 = 1 or 2, +bias b2, act2) -> pointwise + bias + residual + act;
                       the depthwise result never leaves shared memory.  Covers DWConvBlock (model_v2.py:23-39: 3x3, no
                       bias, no act2) and the dw_start -> pw_exp / dw_mid -> pw_proj pairs of timm's
                       UniversalInvertedResidual (backbone called at model_v2.py:266-272)                   */
@@ -72,7 +72,7 @@ typedef struct yl_op {
                         row 64 B, SWIZZLE_64B K-major, two bf16 per float slot), or -1 (older tf32 kernel) */
   int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1 */
   int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv */
-  int32_t reserved;  /* must be 0 */
+  int32_t stride2;   /* YL_OP_DWPW: stride of the depthwise stage (0 or 1 = 1, 2); the output size follows it */
 } yl_op;
 
 /* Build an engine on `device` from a layer program and a HOST weight blob.

@@ -18,7 +18,7 @@ from yololite_b200 import _lib as L, packer  # noqa: E402
 KINDS = {"stem": 0, "conv": 1, "dw": 2, "dwpw": 3, "stem2": 4}
 
 
-def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0):
+def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0, stride2=0):
     g = np.random.RandomState(0)
     blob, off = [], [0]
 
@@ -57,7 +57,7 @@ def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0):
         op.w_off = add(wm)
         op.wt_off = add(packer.tc_image(wm, cout))
         if kind == "dwpw":
-            op.k, op.k2, op.act2 = 1, k2, act2
+            op.k, op.k2, op.act2, op.stride2 = 1, k2, act2, stride2
             op.w2_off = add(g.randn(k2 * k2, cin) / k2)
             op.b2_off = add(packer._pad4(g.randn(cin) * 0.3))
     op.b_off = add(packer._pad4(g.randn(cout)))
@@ -79,13 +79,16 @@ def main():
     ap.add_argument("--tc", type=int, default=1)
     ap.add_argument("--k2", type=int, default=3)
     ap.add_argument("--act2", type=int, default=0)
+    ap.add_argument("--stride2", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
     a = ap.parse_args()
     lib = L.lib()
-    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res, a.k2, a.act2)
+    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res, a.k2, a.act2, a.stride2)
     B, H = a.batch, a.hw
     k = op.k
     ho = (H + 2 * (k // 2) - k) // a.stride + 1
+    if a.kind == "dwpw" and a.stride2 == 2:
+        ho = (H + 2 * (a.k2 // 2) - a.k2) // 2 + 1
     if a.kind == "stem2":
         ho = ((H + 2 - 3) // 2 + 1 + 2 - 3) // 2 + 1
     x = torch.randn((B, 3, H, H) if a.kind in ("stem", "stem2") else (B, H, H, a.cin), device="cuda")

@@ -38,7 +38,7 @@ def run_program(P, x):
                 k2 = op["k2"]
                 w2 = blob[op["w2_off"]:op["w2_off"] + k2 * k2 * cin].reshape(k2, k2, 1, cin).permute(3, 2, 0, 1)
                 b2 = None if op.get("b2_off", -1) < 0 else blob[op["b2_off"]:op["b2_off"] + cin]
-                src = _act(F.conv2d(src, w2, b2, stride=1, padding=k2 // 2, groups=cin), op.get("act2", 0))
+                src = _act(F.conv2d(src, w2, b2, stride=max(1, op.get("stride2", 0)), padding=k2 // 2, groups=cin), op.get("act2", 0))
             ld = (cout + 3) // 4 * 4
             w = blob[op["w_off"]:op["w_off"] + k * k * cin * ld].reshape(k * k * cin, ld)[:, :cout]
             w = w.reshape(k, k, cin, cout).permute(3, 2, 0, 1)

@@ -13,7 +13,7 @@ TOL = 2e-4
 
 
 def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, w2=None, use_tc=1, nchw_input=False,
-         b2=None, act2=0):
+         b2=None, act2=0, stride2=0):
     """w: [Cout,Cin,k,k] torch fp32 (dense) or [C,1,k,k] (depthwise); returns NHWC output (or head layout)."""
     from yololite_b200 import _lib as L, packer
     lib = L.lib()
@@ -49,7 +49,7 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
         if kind == L.OP_DWPW:
             op.k, op.k2 = 1, int(w2.shape[-1])
             op.w2_off = add(np.transpose(w2.double().numpy(), (2, 3, 1, 0)).reshape(op.k2 * op.k2, -1))
-            op.act2 = act2
+            op.act2, op.stride2 = act2, stride2
             if b2 is not None:
                 op.b2_off = add(packer._pad4(b2.double().numpy()))
     op.b_off = add(packer._pad4(bias.double().numpy())) if bias is not None else -1
@@ -60,7 +60,8 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
     kk = 3 if kind == L.OP_DWPW else k
     ho, wo = (Hin + 2 * (k // 2) - k) // stride + 1, (Win + 2 * (k // 2) - k) // stride + 1
     if kind == L.OP_DWPW:
-        ho, wo = Hin, Win
+        s2, k2 = max(1, stride2), int(w2.shape[-1])
+        ho, wo = (Hin + 2 * (k2 // 2) - k2) // s2 + 1, (Win + 2 * (k2 // 2) - k2) // s2 + 1
     out = torch.full((B, ho, wo, cout), float("nan"), device="cuda")
     rs = res.cuda().contiguous() if res is not None else None
     us = up.cuda().contiguous() if up is not None else None
@@ -189,6 +190,23 @@ def test_fused_dw_pw_uir(use_tc, cin, cout, k2, h, w, res):
     mid = F.conv2d(x.permute(0, 3, 1, 2), wd, bd, padding=k2 // 2, groups=cin)
     mid = F.relu(mid) if act2 else mid
     want = _ref(mid, wp, b, 1, 1, act, res=r)
+    assert float((got - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("use_tc", [0, 2])
+@pytest.mark.parametrize("cin,cout,k2,h,w", [(96, 48, 5, 80, 80), (288, 64, 3, 40, 40), (96, 48, 5, 21, 37), (64, 96, 3, 9, 6), (32, 32, 5, 3, 3)])
+def test_fused_dw_pw_stride2(use_tc, cin, cout, k2, h, w):
+    """dw_mid with stride 2 (first block of a stage) fused with pw_proj: depthwise k x k s2 + bias + ReLU -> pointwise + bias."""
+    g = torch.Generator().manual_seed(cin + cout + k2 + h)
+    x = torch.randn(2, h, w, cin, generator=g)
+    wd = torch.randn(cin, 1, k2, k2, generator=g) / k2
+    bd = torch.randn(cin, generator=g) * 0.5
+    wp = torch.randn(cout, cin, 1, 1, generator=g) / cin ** 0.5
+    b = torch.randn(cout, generator=g)
+    got = _run(3, x, wp, b, 1, 1, 0, w2=wd, use_tc=use_tc, b2=bd, act2=1, stride2=2)
+    mid = F.relu(F.conv2d(x.permute(0, 3, 1, 2), wd, bd, stride=2, padding=k2 // 2, groups=cin))
+    want = _ref(mid, wp, b, 1, 1, 0)
+    assert got.shape == want.shape
     assert float((got - want).abs().max()) <= TOL
 
 

@@ -319,8 +319,7 @@ static int launch_conv_gemm_tn(const ConvParams& p, int ldw, cudaStream_t s) {
 }
 
 int launch_dwpw(const ConvParams& p, cudaStream_t s) {
-  YL_REQUIRE(p.w2 && (p.KS == 3 || p.KS == 5) && p.stride == 1 && p.pad == p.KS / 2, "fused depthwise (3x3 / 5x5, s1) + pointwise");
-  YL_REQUIRE(p.Hin == p.Hout && p.Win == p.Wout, "fused DWConvBlock keeps the spatial size");
+  YL_REQUIRE(p.w2 && (p.KS == 3 || p.KS == 5) && (p.stride == 1 || p.stride == 2) && p.pad == p.KS / 2, "fused depthwise (3x3 / 5x5, s1 / s2) + pointwise");
   return launch_conv_gemm(p, s);
 }
 

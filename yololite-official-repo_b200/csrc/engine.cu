@@ -40,7 +40,7 @@ struct yl_engine {
 namespace yl {
 
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
-bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout);
+bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, int dw_stride);
 bool stem2_supported(const ConvParams& c);
 int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st);
 
@@ -59,7 +59,7 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   p.Hu = hu; p.Wu = wu;
   p.act = op.act; p.anchors = op.anchors;
   if (op.kind == YL_OP_DWPW) {                                        // geometry / epilogue of the depthwise stage
-    p.KS = op.k2; p.pad = op.k2 / 2;
+    p.KS = op.k2; p.pad = op.k2 / 2; p.stride = op.stride2 > 1 ? op.stride2 : 1;
     p.b2 = op.b2_off >= 0 ? blob + op.b2_off : nullptr;
     p.act2 = op.act2;
   }
@@ -76,7 +76,7 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
     // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
     // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
     const bool big = (K >= 32 && op.cout >= 32) || use_tc == 2;
-    if (big && (op.cin & 3) == 0 && tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout))
+    if (big && (op.cin & 3) == 0 && tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout, op.kind == YL_OP_DWPW && op.stride2 > 1 ? op.stride2 : 1))
     { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
   }
   ++g_simt_launches;
@@ -113,8 +113,13 @@ static int plan(yl_engine* e, int B, int H, int W) {
       hin = (hin + 2 - 3) / 2 + 1; win = (win + 2 - 3) / 2 + 1;
       YL_REQUIRE(hin >= 1 && win >= 1, "input too small for the network");
     }
-    const int hout = (hin + 2 * pad - op.k) / op.stride + 1;
-    const int wout = (win + 2 * pad - op.k) / op.stride + 1;
+    int hout = (hin + 2 * pad - op.k) / op.stride + 1;
+    int wout = (win + 2 * pad - op.k) / op.stride + 1;
+    if (op.kind == YL_OP_DWPW) {                   // the depthwise stage sets the output size
+      const int s2 = op.stride2 > 1 ? op.stride2 : 1;
+      hout = (hin + 2 * (op.k2 / 2) - op.k2) / s2 + 1;
+      wout = (win + 2 * (op.k2 / 2) - op.k2) / s2 + 1;
+    }
     YL_REQUIRE(hout >= 1 && wout >= 1, "input too small for the network");
     if (op.kind == YL_OP_STEM2) { hin = H; win = W; }
     e->op_hin[i] = hin; e->op_win[i] = win; e->op_hout[i] = hout; e->op_wout[i] = wout;
@@ -187,8 +192,9 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
                "YL_OP_STEM2 needs the tcgen05 weight image, stem weights, 32 stem channels and a 3x3 s2 second conv");
     YL_REQUIRE(op.k >= 1 && (op.k & 1) && op.stride >= 1 && op.cin >= 1 && op.cout >= 1, "bad conv geometry");
     YL_REQUIRE(op.kind != YL_OP_DWPW || ((op.k2 == 3 || op.k2 == 5) && op.k == 1 && op.stride == 1 && op.w2_off >= 0 &&
-                                         op.b2_off < (int64_t)blob_floats && op.act2 >= YL_ACT_NONE && op.act2 <= YL_ACT_SILU),
-               "YL_OP_DWPW: depthwise 3x3 or 5x5 stride 1 followed by a pointwise conv");
+                                         op.b2_off < (int64_t)blob_floats && op.act2 >= YL_ACT_NONE && op.act2 <= YL_ACT_SILU &&
+                                         op.stride2 >= 0 && op.stride2 <= 2),
+               "YL_OP_DWPW: depthwise 3x3 or 5x5 (stride 1 or 2) followed by a pointwise conv");
     YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
     YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
     YL_REQUIRE((op.w_off & 3) == 0 && (op.b_off < 0 || (op.b_off & 3) == 0), "blob offsets must be 16-byte aligned");
@@ -238,7 +244,12 @@ int yl_run_op(const yl_op* op, const float* blob_dev, const float* in, const flo
   const int pad = op->k / 2;
   int hs = Hin, ws = Win;
   if (op->kind == YL_OP_STEM2) { hs = (Hin + 2 - 3) / 2 + 1; ws = (Win + 2 - 3) / 2 + 1; }
-  const int hout = (hs + 2 * pad - op->k) / op->stride + 1, wout = (ws + 2 * pad - op->k) / op->stride + 1;
+  int hout = (hs + 2 * pad - op->k) / op->stride + 1, wout = (ws + 2 * pad - op->k) / op->stride + 1;
+  if (op->kind == YL_OP_DWPW) {
+    const int s2 = op->stride2 > 1 ? op->stride2 : 1;
+    hout = (Hin + 2 * (op->k2 / 2) - op->k2) / s2 + 1;
+    wout = (Win + 2 * (op->k2 / 2) - op->k2) / s2 + 1;
+  }
   return run_op(*op, blob_dev, in, res, up, out, B, Hin, Win, hout, wout, Hu, Wu, use_tensor_cores, sms,
                 reinterpret_cast<cudaStream_t>(stream));
 }

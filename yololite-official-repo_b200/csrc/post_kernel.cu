@@ -36,6 +36,9 @@ struct PostParams {
   float conf;
   double iou;
   int max_det, cap;
+  int direct;             // 1: phase 1 reads the logits straight from global memory (only the objectness logit for the anchors
+                          //    that fail the cheap early-out), 0: streams whole tiles through shared memory
+  int smem_keys;          // candidates per image that can be sorted in shared memory
   // scratch
   int* count;             // [B] candidates
   int* done;              // [B] finished tiles
@@ -104,20 +107,24 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
     float* tile = reinterpret_cast<float*>(smem_raw);
     const float* src = p.lvl[l] + ((size_t)b * p.n_lvl[l] + a0) * D;
     const int n_el = n_tile * D;
-    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
-      const int n4 = n_el >> 2;
-      const float4* s4 = reinterpret_cast<const float4*>(src);
-      float4* d4 = reinterpret_cast<float4*>(tile);
+    if (!p.direct) {
+      if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const int n4 = n_el >> 2;
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(tile);
 #pragma unroll 4
-      for (int i = tid; i < n4; i += POST_THREADS) d4[i] = __ldcs(s4 + i);
-      for (int i = (n4 << 2) + tid; i < n_el; i += POST_THREADS) tile[i] = __ldcs(src + i);
-    } else {
-      for (int i = tid; i < n_el; i += POST_THREADS) tile[i] = __ldcs(src + i);
+        for (int i = tid; i < n4; i += POST_THREADS) d4[i] = __ldcs(s4 + i);
+        for (int i = (n4 << 2) + tid; i < n_el; i += POST_THREADS) tile[i] = __ldcs(src + i);
+      } else {
+        for (int i = tid; i < n_el; i += POST_THREADS) tile[i] = __ldcs(src + i);
+      }
+      __syncthreads();
     }
-    __syncthreads();
 
     if (tid < n_tile) {
-      const float* row = tile + tid * D;
+      // at a detection threshold (conf >= 0.05) almost every anchor fails the objectness early-out: reading 4 of its
+      // 4*(5+C) bytes from global memory beats staging the whole tile
+      const float* row = (p.direct ? src : tile) + tid * D;
       const float so = sigmoid_exact(row[4]);
       if (so > p.conf) {                       // score <= sigmoid(obj): cheap early out
         float score = so;
@@ -179,9 +186,9 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
   const float4* cbox = p.cbox + (size_t)b * p.N;
   unsigned long long* keys;
   unsigned char* flags;        // 0 = alive/undecided, 1 = suppressed, 2 = kept
-  if (M <= POST_SMEM_KEYS) {
+  if (M <= p.smem_keys) {
     keys = reinterpret_cast<unsigned long long*>(smem_raw);
-    flags = smem_raw + (size_t)POST_SMEM_KEYS * 8;
+    flags = smem_raw + (size_t)p.smem_keys * 8;
     int P = 1;
     while (P < M) P <<= 1;
     for (int i = tid; i < P; i += POST_THREADS) keys[i] = i < M ? __ldcg(gkeys + i) : ~0ull;
@@ -436,8 +443,10 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
   p.gflags = s;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   YL_CHECK_CUDA(cudaMemsetAsync(p.count, 0, 2 * (size_t)B * sizeof(int), st));
-  const size_t tile_bytes = (size_t)POST_TILE * D * sizeof(float);
-  const size_t sort_bytes = (size_t)POST_SMEM_KEYS * 9;
+  p.direct = conf >= 0.05f ? 1 : 0;
+  p.smem_keys = p.direct ? POST_SMEM_KEYS / 2 : POST_SMEM_KEYS;
+  const size_t tile_bytes = p.direct ? 0 : (size_t)POST_TILE * D * sizeof(float);
+  const size_t sort_bytes = (size_t)p.smem_keys * 9;
   const size_t smem = (tile_bytes > sort_bytes ? tile_bytes : sort_bytes) + 16;
   YL_REQUIRE(smem <= 200 * 1024, "5+C too large for the shared-memory tile (C <= 195)");
   static thread_local size_t smem_set = 0;

@@ -57,6 +57,8 @@ struct TcParams {
   int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
   int halo_slots;       // MODE 2: halo ring depth
   int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
+  int dw_stride;        // MODE 2: stride of the depthwise stage (1 or 2); the output tile is tile_w x tile_h, the halo covers
+                        // (tile - 1) * stride + KS input pixels per dimension
   int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
   int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
   int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
@@ -553,12 +555,43 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       const int cp = p.nslab * 32;
       const uint32_t hoff = ((uint32_t)(ty * HW + tx0) * 8u + (uint32_t)ch) * 16u;
       const int arow0 = ty * TW + tx0;
+      // stride-2 mapping: patch g = one row of 4 output pixels
+      const bool valid2 = rp < p.tile_h;
+      const uint32_t hoff2 = ((uint32_t)(2 * rp * HW + 2 * tx0) * 8u + (uint32_t)ch) * 16u;
+      const int arow2 = rp * TW + tx0;
       for (int j = grp; j < total; j += 2) {
         const int c_slot = j % HS, c_s = j % p.nslab, stage = j & 1;           // MODE 2 runs with 2 A stages
         const uint32_t hphase = (uint32_t)(j / HS) & 1u, phase = (uint32_t)(j >> 1) & 1u;
         mbar_wait(smem_u32(&hfull_bar[c_slot]), hphase);          // this item's halo tile has landed
         float4 a[8];                                              // [row 0: 4 pixels][row 1: 4 pixels]
-        if (valid) {
+        if (p.dw_stride == 2) {
+          // stride 2: the tile is at most 64 output pixels (rows 64..127 of the MMA tile are unused); a thread owns ONE row of
+          // 4 output pixels = KS rows x (KS + 6) columns of the halo
+          if (valid2) {
+            const unsigned char* hb = halo + (size_t)c_slot * p.halo_bytes + hoff2;
+            const float* wk = w2s + c_s * 32 + ch * 4;
+            {
+              const float4 b4 = *reinterpret_cast<const float4*>(wk + KS * KS * cp);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) a[i] = b4;
+            }
+#pragma unroll
+            for (int ky = 0; ky < KS; ++ky) {
+              float4 h[KS + 6];
+#pragma unroll
+              for (int x = 0; x < KS + 6; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(ky * HW + x) * 128);
+#pragma unroll
+              for (int kx = 0; kx < KS; ++kx) {
+                const float4 w4 = *reinterpret_cast<const float4*>(wk + (ky * KS + kx) * cp);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  a[i].x = fmaf(h[2 * i + kx].x, w4.x, a[i].x); a[i].y = fmaf(h[2 * i + kx].y, w4.y, a[i].y);
+                  a[i].z = fmaf(h[2 * i + kx].z, w4.z, a[i].z); a[i].w = fmaf(h[2 * i + kx].w, w4.w, a[i].w);
+                }
+              }
+            }
+          }
+        } else if (valid) {
           const unsigned char* hb = halo + (size_t)c_slot * p.halo_bytes + hoff;
           const float* wk = w2s + c_s * 32 + ch * 4;
           {
@@ -605,10 +638,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         }
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-        if (valid) {
+        const int nst = p.dw_stride == 2 ? (valid2 ? 4 : 0) : (valid ? 8 : 0);
+        {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int row = arow0 + (i >> 2) * TW + (i & 3);
+            if (i >= nst) break;
+            const int row = p.dw_stride == 2 ? arow2 + i : arow0 + (i >> 2) * TW + (i & 3);
             const uint32_t so = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
             if (p.raw_hi) {          // the tensor core drops the low 13 mantissa bits of hi itself
               float4 l;
@@ -660,8 +695,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         if (i_s == 0) {
           b = i_tile / per_img;
           const int rem = i_tile - b * per_img;
-          y0 = (rem / p.tiles_x) * p.tile_h - PAD;
-          x0 = (rem % p.tiles_x) * p.tile_w - PAD;
+          y0 = (rem / p.tiles_x) * p.tile_h * p.dw_stride - PAD;
+          x0 = (rem % p.tiles_x) * p.tile_w * p.dw_stride - PAD;
         }
         mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1);          // all producer warps are done with item j - HS
         {
@@ -991,21 +1026,23 @@ static bool tc_dense_epi(int N, int anchors, int Nc, int nchunks) { return (N & 
 
 struct TcPlan {
   int Nc = 0, nchunks = 0, stages = 0, halo_slots = 0, wstream = 0, epi2 = 0;
-  int tile_w = TC_TILE_W, tile_h = TC_TILE_H, halo_w = 0, halo_pix = 0, halo_bytes = 0;
+  int tile_w = TC_TILE_W, tile_h = TC_TILE_H, halo_w = 0, halo_h = 0, halo_pix = 0, halo_bytes = 0;
   size_t smem = 0;
 };
 
 // MODE 2 spatial tile: tile_w (multiple of 4) x tile_h <= 128 pixels minimising halo pixels loaded + GEMM rows issued
-static void tc_pick_tile(int ks, int Hout, int Wout, TcPlan* pl) {
+static void tc_pick_tile(int ks, int stride, int Hout, int Wout, TcPlan* pl) {
   long long best = -1;
-  for (int tw = 4; tw <= 128; tw += 4) {
-    const int th = (128 / tw) & ~1;                              // even: a producer thread owns a 2-row patch
-    if (th < 2) continue;
-    const int hp = (tw + ks - 1) * (th + ks - 1);
-    if (hp * 128 > 48 * 1024) continue;                          // keep a ring of >= 2 slots affordable
+  const int maxpix = stride == 2 ? 64 : 128;                   // stride 2: one 4-pixel row per producer thread of a group
+  for (int tw = 4; tw <= maxpix; tw += 4) {
+    const int th = stride == 2 ? maxpix / tw : (maxpix / tw) & ~1;   // stride 1: even, a producer thread owns a 2-row patch
+    if (th < 1 || (stride == 1 && th < 2)) continue;
+    const int hw_ = (tw - 1) * stride + ks, hh_ = (th - 1) * stride + ks;
+    const int hp = hw_ * hh_;
+    if (hp * 128 > 48 * 1024 || hw_ > 256 || hh_ > 256) continue;   // keep a ring of >= 2 slots affordable
     const long long ntile = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
     const long long cost = ntile * (hp + 128);
-    if (best < 0 || cost < best) { best = cost; pl->tile_w = tw; pl->tile_h = th; pl->halo_w = tw + ks - 1; pl->halo_pix = hp; }
+    if (best < 0 || cost < best) { best = cost; pl->tile_w = tw; pl->tile_h = th; pl->halo_w = hw_; pl->halo_h = hh_; pl->halo_pix = hp; }
   }
   pl->halo_bytes = pl->halo_pix * 128;
 }
@@ -1022,13 +1059,15 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   return true;
 }
 
-static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl, bool want_epi2 = false) {
+static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl, bool want_epi2 = false, int dw_stride = 1) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
   const int Npad = (N + 15) / 16 * 16;
   if (mode == 2) {
     if (dw_ks != 3 && dw_ks != 5) return false;
-    tc_pick_tile(dw_ks, Hout, Wout, pl);
+    if (dw_stride != 1 && dw_stride != 2) return false;
+    tc_pick_tile(dw_ks, dw_stride, Hout, Wout, pl);
+    if (pl->halo_pix == 0) return false;
   }
   const size_t dw_bytes = mode == 2 ? (size_t)(dw_ks * dw_ks + 1) * nslab * 32 * 4 : 0;
   for (int nch = 1; nch <= 4; ++nch) {
@@ -1073,9 +1112,9 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
   return false;
 }
 
-bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout) {
+bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, int dw_stride) {
   TcPlan pl;
-  return tc_plan(K, N, anchors, mode, dw_ks, Hout, Wout, &pl);
+  return tc_plan(K, N, anchors, mode, dw_ks, Hout, Wout, &pl, false, dw_stride);
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
@@ -1137,12 +1176,13 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   static const int tma_env = [] { const char* e = getenv("YL_TC_TMA"); return e ? atoi(e) : 1; }();
   static const int epi2_env = [] { const char* e = getenv("YL_TC_EPI2"); return e ? atoi(e) : 1; }();
   const bool tma_a = mode == 0 && tma_env && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0;
-  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl, tma_a && epi2_env),
+  YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl, tma_a && epi2_env, mode == 2 ? c.stride : 1),
              "shape does not fit the tcgen05 conv kernel");
   p.epi2 = pl.epi2;
   p.prod_warps = pl.epi2 ? 4 : TC_PROD_WARPS;
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
   p.tile_w = pl.tile_w; p.tile_h = pl.tile_h; p.halo_w = pl.halo_w; p.halo_pix = pl.halo_pix; p.halo_bytes = pl.halo_bytes;
+  p.dw_stride = mode == 2 ? c.stride : 1;
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE((c.Cin & 3) == 0, "tcgen05 conv needs Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
@@ -1154,7 +1194,8 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   }
   if (mode >= 2) {
     YL_REQUIRE(!c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (mode == 2 || !c.res), "fused depthwise/stem epilogue takes no upsample/head layout");
-    YL_REQUIRE(mode == 3 || (c.stride == 1 && c.Hin == c.Hout && c.Win == c.Wout && c.w2), "fused depthwise -> pointwise keeps the spatial size");
+    YL_REQUIRE(mode == 3 || ((c.stride == 1 || c.stride == 2) && c.w2 && c.Hout == (c.Hin + 2 * (c.KS / 2) - c.KS) / c.stride + 1 &&
+                             c.Wout == (c.Win + 2 * (c.KS / 2) - c.KS) / c.stride + 1), "fused depthwise -> pointwise: depthwise stride 1 or 2");
     p.tiles_x = (c.Wout + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (c.Hout + p.tile_h - 1) / p.tile_h;
     p.num_tiles = c.B * p.tiles_x * p.tiles_y;
@@ -1187,8 +1228,8 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
     p.tma_a = 1;
   }
   if (mode == 2) {
-    YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && p.tile_h + c.KS - 1 <= 256, "halo tile does not fit a TMA box");
-    if (int rc = make_halo_tmap(&tmap, c.in, c.B, c.Hin, c.Win, c.Cin, pl.halo_w, p.tile_h + c.KS - 1)) return rc;
+    YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && pl.halo_h <= 256, "halo tile does not fit a TMA box");
+    if (int rc = make_halo_tmap(&tmap, c.in, c.B, c.Hin, c.Win, c.Cin, pl.halo_w, pl.halo_h)) return rc;
   }
   if (mode == 0) tc_conv_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
   else if (mode == 1) tc_conv_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);

@@ -244,14 +244,14 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     P = Program(cfg=cfg)
 
     def emit(kind, src: Optional[_T], cout, red, k=1, stride=1, act=L.ACT_NONE, w=None, b=None, res: Optional[_T] = None,
-             up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0, w3=None, b2=None, act2=L.ACT_NONE) -> Optional[_T]:
+             up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0, w3=None, b2=None, act2=L.ACT_NONE, stride2=0) -> Optional[_T]:
         dst = None if level is not None else P.new(cout, red)
         P.ops.append(dict(kind=kind, src=(-1 if src is None else src.vid), dst=(-(1 + level) if level is not None else dst.vid),
                           res=(-1 if res is None else res.vid), up=(-1 if up is None else up.vid),
                           cin=(3 if src is None else src.C), cout=cout, k=k, stride=stride, act=act, anchors=anchors, k2=k2,
                           w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
                           w2_off=(-1 if w2 is None else P.add_blob(w2)), w3_off=(-1 if w3 is None else P.add_blob(w3)),
-                          b2_off=(-1 if b2 is None else P.add_blob(_pad4(b2))), act2=act2,
+                          b2_off=(-1 if b2 is None else P.add_blob(_pad4(b2))), act2=act2, stride2=stride2,
                           wt_off=(P.add_blob(tc_image(np.asarray(w, np.float64).reshape(-1, w.shape[-1]), cout))
                                   if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW, L.OP_STEM2) and cout >= 8 and w.shape[0] >= 8 else -1)))
         return dst
@@ -272,8 +272,8 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         w = w * s[:, None, None, None]
         return emit(L.OP_DW, x, x.C, red, k=k, stride=stride, act=act, w=np.transpose(w, (2, 3, 1, 0)).reshape(k * k, -1), b=b)
 
-    def dw_pw_bn(x: _T, dwkey, dwbn, k, act2, pwkey, pwbn, act, red, res=None) -> _T:
-        """stride-1 depthwise k x k + BN (+act2) -> pointwise + BN (+res) (+act) as ONE op (YL_OP_DWPW)."""
+    def dw_pw_bn(x: _T, dwkey, dwbn, k, act2, pwkey, pwbn, act, red, res=None, stride=1) -> _T:
+        """depthwise k x k (stride 1 or 2) + BN (+act2) -> pointwise + BN (+res) (+act) as ONE op (YL_OP_DWPW)."""
         wd = sd.get(dwkey + ".weight")
         sdw, bdw = sd.bn(dwbn)
         wd = wd * sdw[:, None, None, None]
@@ -281,7 +281,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         sp, bp = sd.bn(pwbn)
         wp = wp * sp[:, None, None, None]
         return emit(L.OP_DWPW, x, wp.shape[0], red, k=1, act=act, w=_gemm_w(wp), b=bp, res=res,
-                    w2=np.transpose(wd, (2, 3, 1, 0)).reshape(k * k, -1), k2=k, b2=bdw, act2=act2)
+                    w2=np.transpose(wd, (2, 3, 1, 0)).reshape(k * k, -1), k2=k, b2=bdw, act2=act2, stride2=stride)
 
     # ---------------- backbone
     table, mult, stem_c = BACKBONES[cfg.backbone]
@@ -323,7 +323,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
                 y = x
                 s_start = 1 if km else s
                 fuse_start = bool(ks and fuse_uir and s_start == 1 and x.C % 4 == 0)
-                fuse_mid = bool(km and fuse_uir and s == 1)
+                fuse_mid = bool(km and fuse_uir and s in (1, 2))
                 if fuse_start:
                     y = dw_pw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, L.ACT_NONE,
                                  key + ".pw_exp.conv", key + ".pw_exp.bn", L.ACT_RELU, red)
@@ -332,8 +332,9 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
                         y = dw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, s_start, L.ACT_NONE, red * s_start)
                     y = conv_bn(y, key + ".pw_exp.conv", key + ".pw_exp.bn", 1, 1, L.ACT_RELU, y.red)
                 if fuse_mid:
+                    red *= s
                     x = dw_pw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, L.ACT_RELU,
-                                 key + ".pw_proj.conv", key + ".pw_proj.bn", L.ACT_NONE, red, res=skip)
+                                 key + ".pw_proj.conv", key + ".pw_proj.bn", L.ACT_NONE, red, res=skip, stride=s)
                 else:
                     if km:
                         y = dw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, s, L.ACT_RELU, red * s)
@@ -454,7 +455,7 @@ def to_c(P: Program):
     for i, op in enumerate(P.ops):
         o = arr[i]
         for f in ("kind", "src", "dst", "res", "up", "cin", "cout", "k", "stride", "act", "anchors", "k2", "w_off", "b_off",
-                  "w2_off", "wt_off", "w3_off", "b2_off", "act2"):
+                  "w2_off", "wt_off", "w3_off", "b2_off", "act2", "stride2"):
             setattr(o, f, int(op[f]))
     blob = np.concatenate(P.blob).astype(np.float32, copy=False)
     assert blob.size == P.blob_len
