@@ -70,8 +70,11 @@ typedef struct yl_op {
   int64_t w3_off;    /* YL_OP_STEM2: float offset of the bf16-triple weight image of the fused stem kernel
                         ([9 taps][3 splits][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
                         row 64 B, SWIZZLE_64B K-major, two bf16 per float slot), or -1 (older tf32 kernel) */
-  int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1 */
-  int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv */
+  int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1.
+                        YL_OP_STEM2: float offset of a fused pointwise conv applied after the second conv (timm blocks.0.1):
+                        [cout][cout] weights (k-major, BN folded) followed by cout biases, cout = 16 only; or -1 */
+  int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv;
+                        YL_OP_STEM2: yl_act of the fused pointwise conv */
   int32_t stride2;   /* YL_OP_DWPW: stride of the depthwise stage (0 or 1 = 1, 2); the output size follows it */
 } yl_op;
 

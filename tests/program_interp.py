@@ -30,6 +30,14 @@ def run_program(P, x):
             ld = (cout + 3) // 4 * 4
             w = blob[op["w_off"]:op["w_off"] + 9 * sc * ld].reshape(9 * sc, ld)[:, :cout].reshape(3, 3, sc, cout).permute(3, 2, 0, 1)
             y = F.conv2d(mid, w, bias, stride=s, padding=1)
+            if op.get("b2_off", -1) >= 0:     # fused pointwise conv (same width) after conv2: conv2's act, then 1x1 + bias, act2
+                y = _act(y, op["act"])
+                wq = blob[op["b2_off"]:op["b2_off"] + cout * cout].reshape(cout, cout).t().reshape(cout, cout, 1, 1)
+                bq = blob[op["b2_off"] + cout * cout:op["b2_off"] + cout * cout + cout]
+                y = _act(F.conv2d(y, wq, bq), op.get("act2", 0))
+                if op["dst"] >= 0:
+                    bufs[op["dst"]] = y
+                continue
         elif op["kind"] == 0:
             w = blob[op["w_off"]:op["w_off"] + k * k * cin * cout].reshape(k, k, cin, cout).permute(3, 2, 0, 1)
             y = F.conv2d(src, w, bias, stride=s, padding=k // 2)

@@ -227,12 +227,14 @@ def test_tensor_core_path_is_not_single_pass_tf32():
     assert L.lib().yl_stat(b"simt_launches") == n1 + 1
 
 
-@pytest.mark.parametrize("bf16x3", [True, False])
+@pytest.mark.parametrize("bf16x3,pw", [(True, False), (False, False), (True, True)])
 @pytest.mark.parametrize("hw,n2", [((64, 64), 16), ((45, 52), 16), ((83, 38), 32), ((640, 640), 16), ((96, 100), 12), ((33, 36), 16)])
-def test_fused_stem_conv(hw, n2, bf16x3):
+def test_fused_stem_conv(hw, n2, bf16x3, pw):
     """YL_OP_STEM2: conv_stem (3x3 s2, 3->32, ReLU) -> 3x3 s2 conv (32->n2, ReLU) in one tcgen05 kernel.
     bf16x3 = the bf16-triple kernel (csrc/stem_kernel.cu, w3_off image); otherwise the older 3xTF32 kernel (w3_off = -1)."""
     from yololite_b200 import _lib as L, packer
+    if pw and n2 != 16:
+        pytest.skip("the fused pointwise conv is the 16-channel blocks.0.1 of mobilenetv4_conv_small_050")
     g = torch.Generator().manual_seed(hw[0] + n2)
     B = 2 if hw[0] < 600 else 1
     x = torch.randn(B, 3, hw[0], hw[1], generator=g)
@@ -262,8 +264,15 @@ def test_fused_stem_conv(hw, n2, bf16x3):
     op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(np.concatenate([wsm, bs.double().numpy().reshape(1, -1)]), 32).astype(np.float64)]))
     op.w3_off = add(packer.stem2_image(wm, n2, wsm, bs.double().numpy())) if bf16x3 else -1
     op.b_off = add(packer._pad4(b2.double().numpy()))
+    want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1))
+    if pw:      # blocks.0.1: 1x1 16 -> 16 + bias + ReLU in the output epilogue
+        wq = torch.randn(16, 16, 1, 1, generator=g) / 4
+        bq = torch.randn(16, generator=g)
+        op.b2_off = add(np.concatenate([wq[:, :, 0, 0].t().double().numpy().reshape(-1), bq.double().numpy()]))
+        op.act2 = 1
+        want = F.relu(F.conv2d(want, wq, bq))
+    want = want.permute(0, 2, 3, 1).contiguous()
     dblob = torch.from_numpy(np.concatenate(blob)).cuda()
-    want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1)).permute(0, 2, 3, 1).contiguous()
     out = torch.full(want.shape, float("nan"), device="cuda")
     xc = x.cuda()
     L.check(L.lib().yl_run_op(ctypes.byref(op), dblob.data_ptr(), xc.data_ptr(), None, None, out.data_ptr(), B, hw[0], hw[1], 0, 0, 1, None))

@@ -65,9 +65,12 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   }
   if (op.kind == YL_OP_STEM2) {
     p.Cin = op.k2;                                // K of the second conv = 9 * stem channels
+    p.b2 = op.b2_off >= 0 ? blob + op.b2_off : nullptr;     // fused pointwise conv after conv2 ([cout][cout] + cout biases)
+    p.act2 = op.act2;
     ++g_tc_launches;
     static const int old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
     if (op.w3_off >= 0 && !old_stem && stem2_supported(p)) return launch_stem2(p, blob + op.w3_off, sm_count, st);
+    YL_REQUIRE(!p.b2, "YL_OP_STEM2 with a fused pointwise conv needs the bf16-triple kernel (w3_off, 16 channels, W % 4 == 0)");
     return launch_tc_conv(p, blob + op.wt_off, 3, sm_count, st);
   }
   if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {

@@ -53,6 +53,9 @@ struct Stem2Params {
   float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
   int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
   int tiles_x, tiles_y, num_tiles;
+  const float* __restrict__ pw;        // optional fused pointwise conv after conv2 (timm blocks.0.1): [Cout][Cout] weights (k-major,
+                                       // BN folded) followed by Cout biases; needs Cout == N2 == 16.  nullptr: none
+  int pw_act;
 };
 
 namespace s2 {
@@ -143,13 +146,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
   uint64_t* acc2_full = bars + 16;     // [2]  MMA commit -> epilogue
   uint64_t* acc2_free = bars + 18;     // [2]  epilogue (8 warps) -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  float* pws = reinterpret_cast<float*>(bars + 24);       // fused pointwise: 16 x 16 weights + 16 biases
+  const bool has_pw = p.pw != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS); mbar_init(smem_u32(&a1_empty[s]), 1); }
     for (int j = 0; j < S2_ACC1_RING; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
     mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
     mbar_init(smem_u32(halo_free), 1);
-    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc2_full[b]), 1); mbar_init(smem_u32(&acc2_free[b]), S2_EPI_WARPS); }
+    // with the fused pointwise conv the two column-half warps of a lane quarter take alternate tiles (4 arrivals per buffer)
+    for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc2_full[b]), 1); mbar_init(smem_u32(&acc2_free[b]), has_pw ? S2_EPI_WARPS / 2 : S2_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == S2_MMA_WARP) {
@@ -161,6 +167,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
     for (int i = threadIdx.x; i < total4; i += S2_THREADS)
       reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(p.wimg) + i);
   }
+  if (has_pw)
+    for (int i = threadIdx.x; i < 16 * 16 + 16; i += S2_THREADS) pws[i] = __ldg(p.pw + i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -312,6 +320,52 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
     const uint32_t pl_u = smem_u32(planes);
     auto out_epi = [&](uint32_t it, int tile) {
       const uint32_t b = it & 1u;
+      if (has_pw) {
+        // conv2 (16 ch, bias + act) -> pointwise 16 -> 16 (bias + act) per pixel in registers: this warp reads all 16 columns of
+        // its 32 pixels; the other column-half warp of the lane quarter takes the next tile
+        if ((uint32_t)half != b) return;
+        mbar_wait(smem_u32(&acc2_full[b]), (it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int bi = tile / per_img, rem = tile - bi * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int r = q4 * 32 + lane;
+        const int y = ty * S2_TH + (r >> 3), x = tx * S2_TW + (r & 7);
+        float xin[16];
+        {
+          uint32_t m[16], k[16], k2[16];
+          const uint32_t col = ACC2_COL + S2_ACC2_COLS * b;
+          tmem_ld16(lane_addr + col, m);
+          tmem_ld16(lane_addr + col + 16u, k);
+          tmem_ld16(lane_addr + col + 32u, k2);
+          tmem_ld_wait();
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc2_free[b]));
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            xin[c] = act_fn(__uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c])) + __ldg(p.bias2 + c), p.act);
+        }
+        float yo[16];
+#pragma unroll
+        for (int n = 0; n < 16; ++n) yo[n] = pws[256 + n];
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+#pragma unroll
+          for (int n4 = 0; n4 < 4; ++n4) {
+            const float4 w4 = *reinterpret_cast<const float4*>(pws + kk * 16 + n4 * 4);      // same address in every lane: broadcast
+            yo[4 * n4 + 0] = fmaf(xin[kk], w4.x, yo[4 * n4 + 0]); yo[4 * n4 + 1] = fmaf(xin[kk], w4.y, yo[4 * n4 + 1]);
+            yo[4 * n4 + 2] = fmaf(xin[kk], w4.z, yo[4 * n4 + 2]); yo[4 * n4 + 3] = fmaf(xin[kk], w4.w, yo[4 * n4 + 3]);
+          }
+        }
+        if (y < p.Ho && x < p.Wo) {
+          float* dst = p.out + (((size_t)bi * p.Ho + y) * p.Wo + x) * 16;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(act_fn(yo[4 * g], p.pw_act), act_fn(yo[4 * g + 1], p.pw_act),
+                                                                  act_fn(yo[4 * g + 2], p.pw_act), act_fn(yo[4 * g + 3], p.pw_act));
+        }
+        return;
+      }
       mbar_wait(smem_u32(&acc2_full[b]), (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int bi = tile / per_img, rem = tile - bi * per_img;
@@ -423,7 +477,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
 
 // ---- host side -----------------------------------------------------------------------------------
 static size_t stem2_smem_bytes(int N2) {
-  return (size_t)27 * N2 * 64 + S2_WST_BYTES + 2 * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 + 1024;
+  return (size_t)27 * N2 * 64 + S2_WST_BYTES + 2 * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 + (16 * 16 + 16) * 4 + 1024;
 }
 
 bool stem2_supported(const ConvParams& c) {
@@ -441,6 +495,8 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
   p.Hs = (c.Hin + 2 - 3) / 2 + 1; p.Ws = (c.Win + 2 - 3) / 2 + 1;
   p.Ho = c.Hout; p.Wo = c.Wout; p.Cout = c.Cout; p.N2 = (c.Cout + 15) / 16 * 16; p.act = c.act;
   YL_REQUIRE(stem2_supported(c), "shape does not fit the fused stem kernel");
+  p.pw = c.b2; p.pw_act = c.act2;
+  YL_REQUIRE(!p.pw || (p.Cout == 16 && p.N2 == 16), "fused pointwise after conv2 needs 16 channels");
   p.tiles_x = (p.Wo + S2_TW - 1) / S2_TW;
   p.tiles_y = (p.Ho + S2_TH - 1) / S2_TH;
   const long long nt = (long long)p.B * p.tiles_x * p.tiles_y;

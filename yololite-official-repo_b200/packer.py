@@ -233,7 +233,7 @@ def _pad4(b: np.ndarray) -> np.ndarray:
 
 
 def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True,
-          tensor_cores: bool = True, fuse_stem: bool = True, fuse_uir: Optional[bool] = None) -> Program:
+          tensor_cores: bool = True, fuse_stem: bool = True, fuse_uir: Optional[bool] = None, fuse_pw01: bool = True) -> Program:
     """fuse_dwpw: DWConvBlock (FPN smooth / head trunk) as one op; fuse_uir (default = fuse_dwpw): the stride-1
     depthwise convs of the backbone's UIR blocks ride in the producer stage of the pointwise conv that follows them
     (dw_start -> pw_exp, dw_mid -> pw_proj + residual), so their outputs never reach HBM."""
@@ -290,6 +290,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     # the stem feature itself is never tapped (the FPN takes the last 3-4 taps), so conv_stem can be fused with
     # blocks.0.0 when both are 3x3 s2 and the stem has 32 channels
     fused_stem = bool(fuse_stem and tensor_cores and stem_c == 32 and first[0] == "cn" and first[1] == 3 and first[2] == 2)
+    pw_blob = None
     if fused_stem:
         ws = sd.get(bb + "conv_stem.weight")
         s0, b0 = sd.bn(bb + "bn1")
@@ -298,7 +299,16 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         w1 = sd.get(key + ".conv.weight")
         s1, b1 = sd.bn(key + ".bn1")
         w1m = _gemm_w(w1 * s1[:, None, None, None])
-        x = emit(L.OP_STEM2, None, int(w1.shape[0]), 4, k=3, stride=2, act=L.ACT_RELU, w=w1m,
+        # blocks.0.1 (1x1, same width, BN + ReLU) rides in the output epilogue of the fused kernel when conv2 has 16 channels
+        nxt01 = table[0][1] if len(table[0]) > 1 else None
+        c1 = int(w1.shape[0])
+        pw_blob = None
+        if fuse_pw01 and c1 == 16 and nxt01 is not None and nxt01[0] == "cn" and nxt01[1] == 1 and nxt01[2] == 1 and _round_ch(nxt01[3] * mult) == 16:
+            wq = sd.get(bb + "blocks.0.1.conv.weight")
+            sq, bq = sd.bn(bb + "blocks.0.1.bn1")
+            wq = (wq * sq[:, None, None, None])[:, :, 0, 0]                       # [n][k]
+            pw_blob = np.concatenate([wq.T.reshape(-1), bq.reshape(-1)])          # [k][n] then bias[n]
+        x = emit(L.OP_STEM2, None, c1, 4, k=3, stride=2, act=L.ACT_RELU, w=w1m, b2=pw_blob, act2=(L.ACT_RELU if pw_blob is not None else L.ACT_NONE),
                  w3=stem2_image(w1m, int(w1.shape[0]), ws, b0) if int(w1.shape[0]) <= 32 else None,
                  b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
         feats = [_T(-1, stem_c, 2)]
@@ -310,7 +320,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     for si, stage in enumerate(table):
         for bi, spec in enumerate(stage):
             key = f"{bb}blocks.{si}.{bi}"
-            if fused_stem and si == 0 and bi == 0:
+            if fused_stem and si == 0 and (bi == 0 or (bi == 1 and pw_blob is not None)):
                 pass
             elif spec[0] == "cn":
                 _, k, s, c = spec
