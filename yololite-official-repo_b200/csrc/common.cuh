@@ -1,5 +1,6 @@
 // Shared helpers for the yololite_b200 kernels (sm_100a only).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -70,6 +71,11 @@ struct ConvParams {
   int act2;                          // DWPW: activation between the depthwise and the pointwise stage
   int anchors;                       // >0: head layout [B,A,H,W,D], D = Cout/anchors
 };
+
+// TMA descriptor over an fp32 tensor (tc_gemm.cu): dims / box innermost first, strides in bytes for dims 1..rank-1;
+// out-of-bounds elements read as zero.  cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link).
+int make_tmap_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
+                  const unsigned int* box, bool swizzle128);
 
 // launchers (conv_kernels.cu)
 int launch_stem(const ConvParams& p, cudaStream_t s);

@@ -123,7 +123,7 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t&
 }
 }  // namespace s2
 
-__global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
+__global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params p, const __grid_constant__ CUtensorMap tmap) {
   using namespace s2;
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
@@ -146,12 +146,14 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
   uint64_t* acc2_full = bars + 16;     // [2]  MMA commit -> epilogue
   uint64_t* acc2_free = bars + 18;     // [2]  epilogue (8 warps) -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* patch_full = bars + 21;    //      TMA complete_tx -> producers: the input patch of the next tile has landed
   float* pws = reinterpret_cast<float*>(bars + 24);       // fused pointwise: 16 x 16 weights + 16 biases
   const bool has_pw = p.pw != nullptr;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS); mbar_init(smem_u32(&a1_empty[s]), 1); }
     for (int j = 0; j < S2_ACC1_RING; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
+    mbar_init(smem_u32(patch_full), 1);
     mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
     mbar_init(smem_u32(halo_free), 1);
     // with the fused pointwise conv the two column-half warps of a lane quarter take alternate tiles (4 arrivals per buffer)
@@ -189,30 +191,24 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
       const int k = ch * 8 + m, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
       poff[m] = k < 27 ? (ci * S2_PR + ky) * S2_PP + kx + 1 : (k == 27 ? -1 : -2);
     }
-    const size_t plane = (size_t)p.H * p.W;
+    // the 3 x 67 x 36 input patch (NCHW, zero outside the image = the stem's padding) is ONE TMA box over [B*3][H][W]
     auto issue_patch = [&](int tile) {
-      if (tile < tiles) {
+      if (t == 0 && tile < tiles) {
         const int b = tile / per_img, rem = tile - b * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int iy0 = 4 * S2_TH * ty - 3, ixa = 4 * S2_TW * tx - 4;
-        const float* img = p.in + (size_t)b * 3 * plane;
-        const uint32_t pbase = smem_u32(patch);
-        for (int idx = t; idx < 3 * S2_PR * 9; idx += 32 * S2_PROD_WARPS) {
-          const int row = idx / 9, c4 = idx - row * 9;
-          const int ci = row / S2_PR, iy = iy0 + row - ci * S2_PR, ix = ixa + 4 * c4;
-          const bool ok = iy >= 0 && iy < p.H && ix >= 0 && ix + 3 < p.W;
-          const float* src = ok ? img + ci * plane + (size_t)iy * p.W + ix : p.in;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pbase + (uint32_t)(row * S2_PP + 4 * c4) * 4u), "l"(src),
-                       "r"(ok ? 16u : 0u) : "memory");
-        }
+        const uint32_t bar = smem_u32(patch_full);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)S2_PATCH_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(smem_u32(patch)), "l"(&tmap), "r"(ixa), "r"(iy0), "r"(3 * b), "r"(bar) : "memory");
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     issue_patch(blockIdx.x);
+    uint32_t pphase = 0;
     uint32_t n = 0;                                          // running stem-tile counter -> A1 stage / phase
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");         // patch landed for every producer
+      mbar_wait(smem_u32(patch_full), pphase);               // this tile's patch has landed
+      pphase ^= 1u;
       for (int j = 0; j < S2_MT; ++j, ++n) {
         const uint32_t stage = n & 1u;
         mbar_wait(smem_u32(&a1_empty[stage]), ((n >> 1) & 1u) ^ 1u);
@@ -244,7 +240,6 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(Stem2Params p) {
       asm volatile("bar.sync 1, 256;" ::: "memory");         // every producer is done reading the patch
       issue_patch(tile + gridDim.x);
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
   } else if (warp == S2_MMA_WARP) {
     // =============================== MMA issuer ===============================
     if (lane == 0) {
@@ -509,7 +504,14 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
     attr_set = true;
   }
   int gx = sm_count < p.num_tiles ? sm_count : p.num_tiles;
-  stem2_kernel<<<gx, S2_THREADS, smem, st>>>(p);
+  CUtensorMap tmap;
+  {
+    const unsigned long long dims[3] = {(unsigned long long)p.W, (unsigned long long)p.H, (unsigned long long)p.B * 3};
+    const unsigned long long strides[2] = {(unsigned long long)p.W * 4, (unsigned long long)p.H * p.W * 4};
+    const unsigned int box[3] = {(unsigned)S2_PP, (unsigned)S2_PR, 3};
+    if (int rc = make_tmap_f32(&tmap, p.in, 3, dims, strides, box, false)) return rc;
+  }
+  stem2_kernel<<<gx, S2_THREADS, smem, st>>>(p, tmap);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
