@@ -291,6 +291,8 @@ def run_b200(a):
         hin, win = (S, S) if op["src"] < 0 else hw[op["src"]]
         if op["kind"] == 4:
             ho, wo = out_hw(*out_hw(hin, win, 3, 2), op["k"], op["stride"])
+        elif op["kind"] == 3:      # fused depthwise -> pointwise: the depthwise stage (k2, stride2) sets the output size
+            ho, wo = out_hw(hin, win, op["k2"], max(1, op.get("stride2", 0)))
         else:
             ho, wo = out_hw(hin, win, op["k"], op["stride"])
         if op["dst"] >= 0:

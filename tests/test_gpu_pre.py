@@ -12,7 +12,7 @@ cv2 = pytest.importorskip("cv2")
 
 
 @pytest.mark.parametrize("shape,S", [((360, 500), 320), ((100, 37), 320), ((33, 77), 96), ((500, 360), 640), ((640, 640), 640),
-                                     ((720, 1280), 640)])
+                                     ((720, 1280), 640), ((400, 640), 640), ((640, 302), 640), ((96, 96), 96)])
 def test_preprocess_bit_exact(shape, S):
     import yololite_b200 as y
     img = np.random.RandomState(shape[0]).randint(0, 256, (shape[0], shape[1], 3)).astype(np.uint8)

@@ -69,6 +69,55 @@ __global__ void __launch_bounds__(256) pre_kernel(PreParams p) {
   }
 }
 
+// Fast path when the letterbox does not resize (nh == h0, nw == w0): a thread converts 4 horizontally adjacent output pixels.
+// The 256 possible byte values per channel go through a shared-memory table built with the SAME IEEE operations
+// (v / 255, then (v - mean) / std), so the result is bit-identical to the general kernel and to the reference's fp32 math.
+__global__ void __launch_bounds__(256) pre_kernel_copy4(PreParams p) {
+  __shared__ float lut[3][256];
+  {
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fdiv_rn((float)threadIdx.x, 255.f);
+      lut[c][threadIdx.x] = __fdiv_rn(__fsub_rn(v, mean[c]), stdv[c]);
+    }
+  }
+  __syncthreads();
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int y = blockIdx.y;
+  if (x >= p.S) return;
+  p.src += (size_t)blockIdx.z * p.src_stride;
+  p.dst += (size_t)blockIdx.z * p.dst_stride;
+  const int ry = y - p.top;
+  unsigned char px[4][3];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rx = x + i - p.left;
+    if (ry >= 0 && ry < p.nh && rx >= 0 && rx < p.nw) {
+      const unsigned char* s = p.src + (size_t)ry * p.pitch + rx * 3;
+      px[i][0] = s[0]; px[i][1] = s[1]; px[i][2] = s[2];
+    } else {
+      px[i][0] = px[i][1] = px[i][2] = 114;
+    }
+  }
+  const size_t plane = (size_t)p.S * p.S;
+  float* o = p.dst + (size_t)y * p.S + x;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)      // output channel c = RGB -> source channel 2-c
+    *reinterpret_cast<float4*>(o + c * plane) = make_float4(lut[c][px[0][2 - c]], lut[c][px[1][2 - c]], lut[c][px[2][2 - c]], lut[c][px[3][2 - c]]);
+}
+
+static void launch_pre(const PreParams& p, int B, cudaStream_t st) {
+  if (p.nh == p.h0 && p.nw == p.w0 && (p.S & 3) == 0 && (reinterpret_cast<uintptr_t>(p.dst) & 15) == 0 && (p.dst_stride & 3) == 0) {
+    dim3 grid((p.S / 4 + 255) / 256, p.S, B);
+    pre_kernel_copy4<<<grid, 256, 0, st>>>(p);
+  } else {
+    dim3 grid((p.S + 255) / 256, p.S, B);
+    pre_kernel<<<grid, 256, 0, st>>>(p);
+  }
+}
+
 }  // namespace yl
 
 extern "C" int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t pitch, float* dst, int32_t S, int32_t nh,
@@ -78,8 +127,7 @@ extern "C" int yl_preprocess(const uint8_t* src, int32_t h0, int32_t w0, int32_t
   YL_REQUIRE(h0 >= 1 && w0 >= 1 && pitch >= w0 * 3 && S >= 1, "bad image geometry");
   YL_REQUIRE(nh >= 1 && nw >= 1 && left >= 0 && top >= 0 && left + nw <= S && top + nh <= S, "letterbox does not fit");
   PreParams p{src, dst, h0, w0, pitch, S, nh, nw, left, top, 0, 0};
-  dim3 grid((S + 255) / 256, S);
-  pre_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pre(p, 1, reinterpret_cast<cudaStream_t>(stream));
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -91,8 +139,7 @@ extern "C" int yl_preprocess_batch(const uint8_t* src, int32_t B, int32_t h0, in
   YL_REQUIRE(h0 >= 1 && w0 >= 1 && S >= 1, "bad image geometry");
   YL_REQUIRE(nh >= 1 && nw >= 1 && left >= 0 && top >= 0 && left + nw <= S && top + nh <= S, "letterbox does not fit");
   PreParams p{src, dst, h0, w0, w0 * 3, S, nh, nw, left, top, (size_t)h0 * w0 * 3, (size_t)3 * S * S};
-  dim3 grid((S + 255) / 256, S, B);
-  pre_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  launch_pre(p, B, reinterpret_cast<cudaStream_t>(stream));
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
