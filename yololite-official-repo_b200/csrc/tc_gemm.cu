@@ -59,6 +59,7 @@ struct TcParams {
   int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
   int dw_stride;        // MODE 2: stride of the depthwise stage (1 or 2); the output tile is tile_w x tile_h, the halo covers
                         // (tile - 1) * stride + KS input pixels per dimension
+  int halo_tx;          // MODE 1 + TMA: exact bytes of one halo box (the slot stride halo_bytes is rounded up to 128)
   int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
   int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
   int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   unsigned char* a_ring = w_lo + (size_t)w_slabs * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
   unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x halo_bytes
   // MODE 3: `halo` region = stem weight image (hi 4 KB, lo 4 KB) | stem-output halo (71808 B) | input patch (28560 B)
-  float* w2s = reinterpret_cast<float*>(halo + (MODE == 2 ? (size_t)p.halo_slots * p.halo_bytes : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
+  float* w2s = reinterpret_cast<float*>(halo + ((MODE == 2 || (MODE == 1 && p.tma_a)) ? (size_t)p.halo_slots * p.halo_bytes : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
   // MODE 2: depthwise taps [KS*KS][nslab*32] followed by the depthwise bias row
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)(KS * KS + 1) * p.nslab * 32 * 4 : 0));
   uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
     mbar_init(smem_u32(halo_full), 4);
     mbar_init(smem_u32(halo_empty), TC_PROD_WARPS);
-    for (int s = 0; s < TC_MAX_HALO_SLOTS; ++s) { mbar_init(smem_u32(&hfull_bar[s]), 1); mbar_init(smem_u32(&hempty_bar[s]), 4); }
+    for (int s = 0; s < TC_MAX_HALO_SLOTS; ++s) { mbar_init(smem_u32(&hfull_bar[s]), 1); mbar_init(smem_u32(&hempty_bar[s]), MODE == 2 ? 4 : TC_PROD_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_MMA_WARP) {
@@ -431,6 +432,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    } else if (MODE == 1 && p.tma_a) {
+      // Dense KxK conv with a small Cin (timm blocks.1.0: 3x3 s2, 16 -> 48): the whole-Cin halo of the INPUT for one spatial
+      // tile of 8 x 16 output pixels arrives as ONE TMA box; the im2col K-slabs are gathered shared -> shared (a 16 B piece
+      // never straddles a tap because Cin % 4 == 0), hi = raw fp32, lo = a - trunc_tf32(a).
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int HS = p.halo_slots, HW = p.halo_w;
+      const int pix_bytes = c.Cin * 4;
+      uint32_t soff[4];
+      int hp0[4];                                     // halo pixel of tap (0,0) for this thread's 4 output rows
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = r0 + 32 * i;
+        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
+        hp0[i] = (row / p.tile_w) * c.stride * HW + (row % p.tile_w) * c.stride;
+      }
+      int stage = 0, slot = 0;
+      uint32_t phase = 0, hphase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        mbar_wait(smem_u32(&hfull_bar[slot]), hphase);            // this tile's halo has landed
+        const unsigned char* hb = halo + (size_t)slot * p.halo_bytes;
+        for (int s = 0; s < p.nslab; ++s) {
+          const int k0 = s * 32 + ch * 4;
+          const int tap = k0 / c.Cin, ci = k0 - tap * c.Cin;
+          const int ky = tap / c.KS, kx = tap - ky * c.KS;
+          const int toff = (ky * HW + kx) * pix_bytes + ci * 4;
+          float4 a[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            a[i] = k0 < p.K ? *reinterpret_cast<const float4*>(hb + (size_t)hp0[i] * pix_bytes + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 l;
+            l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
+            l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
+            l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
+            l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(hi + soff[i]) = a[i];                 // the tensor core drops the low 13 bits itself
+            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&hempty_bar[slot]));   // this warp no longer reads the halo
+        if (++slot == HS) { slot = 0; hphase ^= 1; }
       }
     } else if (MODE != 2) {
       // cp.async pipeline: the 16 B pieces are copied global -> shared (zero-filled outside the image / past K) straight
@@ -681,6 +732,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       }
     }
     __syncwarp();
+  } else if (MODE == 1 && warp == TC_TMA_WARP) {
+    // =============================== TMA issuer (MODE 1: whole-Cin halo per tile) ===============================
+    if (p.tma_a && lane == 0) {
+      const int per_img = p.tiles_x * p.tiles_y;
+      int slot = 0;
+      uint32_t hphase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int b = tile / per_img, rem = tile - b * per_img;
+        const int y0 = (rem / p.tiles_x) * p.tile_h * c.stride - c.pad, x0 = (rem % p.tiles_x) * p.tile_w * c.stride - c.pad;
+        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1);
+        const uint32_t bar = smem_u32(&hfull_bar[slot]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.halo_tx) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(smem_u32(halo) + (uint32_t)slot * (uint32_t)p.halo_bytes), "l"(&tmap), "r"(0), "r"(x0), "r"(y0), "r"(b), "r"(bar)
+            : "memory");
+        if (++slot == p.halo_slots) { slot = 0; hphase ^= 1; }
+      }
+    }
+    __syncwarp();
   } else if (MODE == 2 && warp == TC_TMA_WARP) {
     // =============================== TMA issuer (MODE 2) ===============================
     if (lane == 0) {
@@ -816,13 +887,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     const int tile_step = p.epi2 ? 2 * (int)gridDim.x : (int)gridDim.x;
     for (int tile = blockIdx.x + (p.epi2 ? grp * (int)gridDim.x : 0); tile < tiles; tile += tile_step) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
-      const int rows_ok = MODE >= 2 ? 32 : min(32, M - mw);   // rows of this warp inside the matrix
+      const bool spatial = MODE >= 2 || (MODE == 1 && p.tma_a);   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
+      const int rows_ok = spatial ? 32 : min(32, M - mw);      // rows of this warp inside the matrix
       // element offset of the output row for each of the 8 rows this lane owns, -1 = outside
       int orow[8];
-      if (MODE >= 2) {
+      if (spatial) {
         const int per_img = p.tiles_x * p.tiles_y;
         const int b = tile / per_img, rem = tile - b * per_img;
-        const int TW = MODE == 2 ? p.tile_w : TC_TILE_W, TH = MODE == 2 ? p.tile_h : TC_TILE_H;
+        const int TW = MODE == 3 ? TC_TILE_W : p.tile_w, TH = MODE == 3 ? TC_TILE_H : p.tile_h;
         const int y0 = (rem / p.tiles_x) * TH, x0 = (rem % p.tiles_x) * TW;
         int ry = (q * 32 + vr) / TW, rx = (q * 32 + vr) - ry * TW;      // rows vr + 4*it: step 4 pixels (TW % 4 == 0)
 #pragma unroll
@@ -1207,6 +1279,30 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
     p.Hs = (c.Hin + 2 - 3) / 2 + 1;
     p.Ws = (c.Win + 2 - 3) / 2 + 1;
   }
+  // MODE 1 with a small Cin: whole-Cin halo tiles by TMA + shared-memory im2col (see the producer branch)
+  size_t smem_override = 0;
+  if (mode == 1 && tma_env && pl.nchunks == 1 && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (c.Cin & 3) == 0 && c.Cin <= 64 &&
+      (c.stride == 1 || c.stride == 2) && c.pad == c.KS / 2 && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0) {
+    const int tw = TC_TILE_W, th = TC_TILE_H;
+    const int hw_ = (tw - 1) * c.stride + c.KS, hh_ = (th - 1) * c.stride + c.KS;
+    const size_t hexact = (size_t)hw_ * hh_ * c.Cin * 4;
+    const size_t hbytes = (hexact + 127) / 128 * 128;
+    const size_t fixed = (size_t)2 * p.nslab * pl.Nc * 128 + TC_AUX_BYTES + 1024;
+    if (hw_ <= 256 && hh_ <= 256 && fixed + 2 * hbytes + 2 * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) {
+      p.tma_a = 1;
+      pl.epi2 = 0;
+      p.tile_w = tw; p.tile_h = th; p.halo_w = hw_; p.halo_pix = hw_ * hh_; p.halo_bytes = (int)hbytes; p.halo_tx = (int)hexact;
+      p.halo_slots = 2;
+      int stages = (int)((TC_SMEM_BUDGET - fixed - 2 * hbytes) / (2 * TC_SLAB_BYTES));
+      p.stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
+      if (fixed + 3 * hbytes + (size_t)p.stages * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) p.halo_slots = 3;
+      smem_override = fixed + (size_t)p.halo_slots * hbytes + (size_t)p.stages * 2 * TC_SLAB_BYTES;
+      p.tiles_x = (c.Wout + tw - 1) / tw;
+      p.tiles_y = (c.Hout + th - 1) / th;
+      p.num_tiles = c.B * p.tiles_x * p.tiles_y;
+      p.dense_epi = 0;
+    }
+  }
   if (mode >= 2) {
     YL_REQUIRE(!c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (mode == 2 || !c.res), "fused depthwise/stem epilogue takes no upsample/head layout");
     YL_REQUIRE(mode == 3 || ((c.stride == 1 || c.stride == 2) && c.w2 && c.Hout == (c.Hin + 2 * (c.KS / 2) - c.KS) / c.stride + 1 &&
@@ -1222,7 +1318,7 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   while (cols < 4 * p.Nc) cols <<= 1;
   if (mode == 3) { YL_REQUIRE(p.Nc <= 32, "fused stem kernel: N chunk <= 32"); cols = 128; }
   p.tmem_cols = cols;
-  const size_t smem = pl.smem;
+  const size_t smem = smem_override ? smem_override : pl.smem;
   static thread_local bool attr_set = false;
   if (!attr_set) {
     YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1241,6 +1337,12 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   if (tma_a) {
     if (int rc = make_a_tmap(&tmap, c.in, p.M, c.Cin)) return rc;
     p.tma_a = 1;
+  }
+  if (mode == 1 && p.tma_a) {
+    const unsigned long long dims[4] = {(unsigned long long)c.Cin, (unsigned long long)c.Win, (unsigned long long)c.Hin, (unsigned long long)c.B};
+    const unsigned long long strides[3] = {(unsigned long long)c.Cin * 4, (unsigned long long)c.Win * c.Cin * 4, (unsigned long long)c.Hin * c.Win * c.Cin * 4};
+    const unsigned int box[4] = {(unsigned)c.Cin, (unsigned)p.halo_w, (unsigned)(p.halo_pix / p.halo_w), 1};
+    if (int rc = make_tmap_f32(&tmap, c.in, 4, dims, strides, box, false)) return rc;
   }
   if (mode == 2) {
     YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && pl.halo_h <= 256, "halo tile does not fit a TMA box");
