@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   // ---- shared memory carve-up (all slabs 1024 B aligned)
   const uint32_t w_slab_bytes = (uint32_t)p.Nc * 128u;
   // resident weights: [hi: nslab slabs][lo: nslab slabs]; streamed (MODE 2, p.wstream): stages x (hi slab, lo slab)
-  const int w_slabs = (MODE == 2 && p.wstream) ? p.stages : p.nslab;
+  const int w_slabs = p.wstream ? p.stages : p.nslab;
   unsigned char* w_hi = smem;
   unsigned char* w_lo = w_hi + (size_t)w_slabs * w_slab_bytes;
   unsigned char* a_ring = w_lo + (size_t)w_slabs * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
@@ -217,7 +217,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   uint64_t* wfull_bar = tempty_bar + 4;            // [stages]   MODE 2 streamed weights: cp.async.bulk complete_tx -> MMA
   uint64_t* hfull_bar = wfull_bar + TC_MAX_STAGES;   // [halo_slots] MODE 2: TMA complete_tx -> producers
   uint64_t* hempty_bar = hfull_bar + TC_MAX_HALO_SLOTS;   // [halo_slots] MODE 2: producers (8 warps) -> TMA thread
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hempty_bar + TC_MAX_HALO_SLOTS);
+  uint64_t* wres_bar = hempty_bar + TC_MAX_HALO_SLOTS;   // resident weight image: cp.async.bulk complete_tx -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 2);   // keeps the staging area behind it 16 B aligned
   float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 rows x TC_EPI_PITCH floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
@@ -231,23 +232,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     mbar_init(smem_u32(halo_full), 4);
     mbar_init(smem_u32(halo_empty), TC_PROD_WARPS);
     for (int s = 0; s < TC_MAX_HALO_SLOTS; ++s) { mbar_init(smem_u32(&hfull_bar[s]), 1); mbar_init(smem_u32(&hempty_bar[s]), MODE == 2 ? 4 : TC_PROD_WARPS); }
+    mbar_init(smem_u32(wres_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // resident weight image (hi then lo, every slab's rows [chunk_n0, chunk_n0 + Nc)): bulk copies straight from the
+    // pre-swizzled image in L2, asynchronous -- only the MMA thread waits for them, before its first instruction
+    if (!p.wstream) {
+      const int rows = min(p.Nc, p.Npad - chunk_n0);              // rows of this chunk that exist in the image
+      const uint32_t bar = smem_u32(wres_bar);
+      if (p.nchunks == 1) {                                         // the whole image is one contiguous block
+        const uint32_t bytes = 2u * (uint32_t)p.nslab * w_slab_bytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(w_hi)), "l"(p.wimg), "r"(bytes), "r"(bar) : "memory");
+      } else {
+        const uint32_t bytes = (uint32_t)rows * 128u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * (uint32_t)p.nslab * bytes) : "memory");
+        for (int ps = 0; ps < 2 * p.nslab; ++ps)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(smem_u32(w_hi) + (uint32_t)ps * w_slab_bytes), "l"(p.wimg + ((size_t)ps * p.Npad + chunk_n0) * 32), "r"(bytes), "r"(bar)
+                       : "memory");
+      }
+    }
   }
   if (warp == TC_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // resident weight image: hi then lo, every slab's rows [chunk_n0, chunk_n0+Nc)
-  if (!(MODE == 2 && p.wstream)) {
-    const int per_slab4 = p.Nc * 8;                                 // float4 per slab
-    const int total4 = 2 * p.nslab * per_slab4;
-    for (int i = threadIdx.x; i < total4; i += TC_THREADS) {
-      const int ps = i / per_slab4, r = i - ps * per_slab4;          // ps = pass*nslab + slab
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (chunk_n0 + (r >> 3) < p.Npad)
-        v = __ldg(reinterpret_cast<const float4*>(p.wimg) + ((size_t)ps * p.Npad + chunk_n0) * 8 + r);
-      reinterpret_cast<float4*>(w_hi)[(size_t)ps * per_slab4 + r] = v;
+  // rows of a partial last chunk that lie past the image are zero (generic stores; disjoint from the bulk copies)
+  if (!p.wstream && chunk_n0 + p.Nc > p.Npad) {
+    const int rows = p.Npad - chunk_n0, zr = p.Nc - rows;          // zr zero rows at the end of every slab
+    for (int i = threadIdx.x; i < 2 * p.nslab * zr * 8; i += blockDim.x) {
+      const int ps = i / (zr * 8), r = i - ps * (zr * 8);
+      reinterpret_cast<float4*>(w_hi + (size_t)ps * w_slab_bytes + (size_t)rows * 128)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   if (MODE == 3) {   // stem weight image [2][32 rows][32 k], pre-swizzled, right after the 27x32 weights + 32 biases
@@ -723,10 +740,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TC_SLAB_BYTES) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                       "r"((uint32_t)TC_SLAB_BYTES + (p.wstream ? 2u * w_slab_bytes : 0u)) : "memory");
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                        ::"r"(smem_u32(a_ring) + (uint32_t)stage * 2u * TC_SLAB_BYTES), "l"(&tmap), "r"(s * 32), "r"(tile * TC_BM), "r"(bar)
                        : "memory");
+          if (p.wstream) {          // K too long for a resident weight image: this K-slab of W (hi, lo) rides with the A tile
+#pragma unroll
+            for (int ps = 0; ps < 2; ++ps)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes), "l"(p.wimg + ((size_t)ps * p.nslab + s) * p.Npad * 32),
+                             "r"(w_slab_bytes), "r"(bar) : "memory");
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -809,6 +834,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t buf_stride = MODE == 3 ? 64u : (uint32_t)(2 * p.Nc);
+      if (!p.wstream) mbar_wait(smem_u32(wres_bar), 0);          // the resident weight image has landed
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         if (MODE == 3) {            // five stem GEMM tiles (K = 32, N = 32) against the resident stem weight image
           const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
@@ -844,8 +870,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           const uint32_t a_lo = a_hi + TC_SLAB_BYTES;
           uint32_t b_hi = smem_u32(w_hi + (size_t)s * w_slab_bytes);
           uint32_t b_lo = smem_u32(w_lo + (size_t)s * w_slab_bytes);
-          if (MODE == 2 && p.wstream) {
-            mbar_wait(smem_u32(&wfull_bar[stage]), phase);     // this stage's W slabs have landed (async proxy write)
+          if (p.wstream) {
+            // this stage's W slabs: MODE 2 waits for them here; in MODE 0 they share the A tile's barrier, which the
+            // producers have already waited on
+            if (MODE == 2) mbar_wait(smem_u32(&wfull_bar[stage]), phase);
             b_hi = smem_u32(w_hi) + (uint32_t)(stage * 2) * w_slab_bytes;
             b_lo = b_hi + w_slab_bytes;
           }
@@ -1184,6 +1212,22 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
   return false;
 }
 
+// MODE 0 with TMA-fed A tiles and a K too long for a resident weight image at one N chunk: every stage carries its own
+// K-slab of W (hi, lo) next to the A tile.  Returns false when it does not fit.
+static bool tc_plan_stream0(int N, int anchors, TcPlan* pl) {
+  const int Npad = (N + 15) / 16 * 16;
+  if (Npad > 128) return false;
+  const size_t dense_bytes = tc_dense_epi(N, anchors, Npad, 1) ? (size_t)4 * 32 * Npad * 4 : 0;
+  const size_t fixed = TC_AUX_BYTES + dense_bytes + 1024;
+  const size_t per_stage = (size_t)2 * TC_SLAB_BYTES + (size_t)2 * Npad * 128;
+  int stages = (int)((TC_SMEM_BUDGET - fixed) / per_stage);
+  if (stages < 2) return false;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  pl->Nc = Npad; pl->nchunks = 1; pl->wstream = 1; pl->stages = stages; pl->halo_slots = 0; pl->epi2 = 0;
+  pl->smem = fixed + stages * per_stage;
+  return true;
+}
+
 bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, int dw_stride) {
   TcPlan pl;
   return tc_plan(K, N, anchors, mode, dw_ks, Hout, Wout, &pl, false, dw_stride);
@@ -1265,6 +1309,10 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   const bool tma_a = mode == 0 && tma_env && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0;
   YL_REQUIRE(tc_plan(p.K, c.Cout, c.anchors, mode, mode == 2 ? c.KS : 0, c.Hout, c.Wout, &pl, tma_a && epi2_env, mode == 2 ? c.stride : 1),
              "shape does not fit the tcgen05 conv kernel");
+  if (tma_a && pl.nchunks > 1) {             // N was chunked only because the weights do not fit: stream them instead
+    TcPlan ps;
+    if (tc_plan_stream0(c.Cout, c.anchors, &ps)) pl = ps;
+  }
   p.epi2 = pl.epi2;
   p.prod_warps = pl.epi2 ? 4 : TC_PROD_WARPS;
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
