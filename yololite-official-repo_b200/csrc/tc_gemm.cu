@@ -46,7 +46,9 @@ constexpr int S3_PATCH_H = 2 * S3_HALO_H + 1, S3_PATCH_W = 2 * S3_HALO_W + 1, S3
 constexpr int S3_PATCH_BYTES = 3 * S3_PATCH_H * S3_PATCH_PITCH * 4;      // 28560
 constexpr int S3_HALO_BYTES = S3_HALO_PIX * 128;                        // 71808
 constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
-constexpr int TC_AUX_BYTES = 256 + 4 * 32 * TC_EPI_PITCH * 4;   // barriers + tmem slot + epilogue transpose staging
+constexpr int TC_STG_BYTES = 5120;                    // per epilogue warp: the padded transpose tile (32 x 36 floats) or the 4 KB
+                                                      // SWIZZLE_128B tile a TMA store reads; 1024 B aligned
+constexpr int TC_AUX_BYTES = 256 + 512 + 4 * TC_STG_BYTES;      // barriers + tmem slot, bias vector, epilogue staging (one group)
 
 struct TcParams {
   ConvParams c;
@@ -63,6 +65,8 @@ struct TcParams {
   int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
   int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
   int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
+  int stg_stride;       // bytes of epilogue staging per warp (TC_STG_BYTES; the smem-starved MODE 3 packs them at 4608)
+  int tma_out;          // epilogue writes each warp's 32 x 32 block through a swizzled staging tile + TMA tensor store
   int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
   int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
                         // streamed from L2 into the A stage's own W slot with cp.async.bulk
@@ -189,7 +193,8 @@ __device__ __forceinline__ float4 load_a(const ConvParams& c, const float* rbase
 }
 
 template <int MODE, int KS>
-__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap,
+                                                                const __grid_constant__ CUtensorMap omap) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -203,7 +208,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   unsigned char* w_hi = smem;
   unsigned char* w_lo = w_hi + (size_t)w_slabs * w_slab_bytes;
   unsigned char* a_ring = w_lo + (size_t)w_slabs * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
-  unsigned char* halo = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;           // MODE 2: halo_slots x halo_bytes
+  unsigned char* stage_base = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;     // epilogue staging, 1024 B aligned
+  unsigned char* halo = stage_base + (size_t)(p.epi2 ? 8 : 4) * p.stg_stride;     // MODE 2: halo_slots x halo_bytes
   // MODE 3: `halo` region = stem weight image (hi 4 KB, lo 4 KB) | stem-output halo (71808 B) | input patch (28560 B)
   float* w2s = reinterpret_cast<float*>(halo + ((MODE == 2 || (MODE == 1 && p.tma_a)) ? (size_t)p.halo_slots * p.halo_bytes : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
   // MODE 2: depthwise taps [KS*KS][nslab*32] followed by the depthwise bias row
@@ -219,7 +225,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   uint64_t* hempty_bar = hfull_bar + TC_MAX_HALO_SLOTS;   // [halo_slots] MODE 2: producers (8 warps) -> TMA thread
   uint64_t* wres_bar = hempty_bar + TC_MAX_HALO_SLOTS;   // resident weight image: cp.async.bulk complete_tx -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 2);   // keeps the staging area behind it 16 B aligned
-  float* epi_stage = reinterpret_cast<float*>(tmem_slot + 4);      // 4 warps x 32 rows x TC_EPI_PITCH floats
+  float* bias_s = reinterpret_cast<float*>(tmem_slot + 4);         // bias of this CTA's N chunk (128 floats)
+  float* dense_stage = bias_s + 128;                               // dense epilogue only: 4 warps x 32 x Nc floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
 
@@ -267,6 +274,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       reinterpret_cast<float4*>(w_hi + (size_t)ps * w_slab_bytes + (size_t)rows * 128)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_s[i] = (c.bias && i < p.Nc && chunk_n0 + i < c.Cout) ? __ldg(c.bias + chunk_n0 + i) : 0.f;
   if (MODE == 3) {   // stem weight image [2][32 rows][32 k], pre-swizzled, right after the 27x32 weights + 32 biases
     for (int i = threadIdx.x; i < 512; i += TC_THREADS)
       reinterpret_cast<float4*>(halo)[i] = __ldg(reinterpret_cast<const float4*>(c.w2 + 896) + i);
@@ -903,11 +911,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     const int grp = warp >= TC_EPI_WARP0 ? 0 : 1;
     const int N = c.Cout;
     const int D = c.anchors > 0 ? N / c.anchors : N;
-    float* stg = epi_stage + (grp * 4 + q) * (32 * TC_EPI_PITCH);
+    unsigned char* sb = stage_base + (size_t)(grp * 4 + q) * p.stg_stride;
+    float* stg = reinterpret_cast<float*>(sb);
     const bool vec = (N & 3) == 0 && c.anchors <= 1;
     // dense staging: N not a multiple of 4 (head outputs, 5+C channels), single chunk, plain [M][N] output
     const bool dense = p.dense_epi != 0;
-    float* dstg = epi_stage + 4 * 32 * TC_EPI_PITCH + q * (32 * p.Nc);
+    float* dstg = dense_stage + q * (32 * p.Nc);
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
     int acc = p.epi2 ? grp : 0;
@@ -917,6 +926,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
       const bool spatial = MODE >= 2 || (MODE == 1 && p.tma_a);   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
       const int rows_ok = spatial ? 32 : min(32, M - mw);      // rows of this warp inside the matrix
+      if (MODE != 3 && p.tma_out) {
+        // TMEM -> registers (lane = row) -> +bias, act -> SWIZZLE_128B staging tile (conflict-free 16 B stores) -> ONE TMA tensor
+        // store per warp and 32-column block; rows / columns outside the tensor are clipped by the hardware
+        int c1 = mw, c2 = 0, c3 = 0;
+        bool wvalid = mw < M;
+        if (spatial) {
+          const int per_img = p.tiles_x * p.tiles_y;
+          const int b = tile / per_img, rem = tile - b * per_img;
+          const int rpw = 32 / p.tile_w;                       // tile rows covered by one warp (tile_w divides 32)
+          c1 = (rem % p.tiles_x) * p.tile_w; c2 = (rem / p.tiles_x) * p.tile_h + q * rpw; c3 = b;
+          wvalid = q * rpw < p.tile_h && c2 < c.Hout;
+        }
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
+        for (int col = 0; col < p.Nc; col += 32) {
+          float4 o[8];
+          {
+            uint32_t v[32], w[32];
+            if (p.Nc - col > 16) {
+              tmem_ld32_nowait(taddr + (uint32_t)col, v);
+              tmem_ld32_nowait(taddr + (uint32_t)(p.Nc + col), w);
+              tmem_ld_wait();
+            } else {
+              float a[16], b[16];
+              tmem_ld16(taddr + (uint32_t)col, a);
+              tmem_ld16(taddr + (uint32_t)(p.Nc + col), b);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { v[j] = __float_as_uint(a[j]); w[j] = __float_as_uint(b[j]); v[16 + j] = 0; w[16 + j] = 0; }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bia = col + 4 * j < 128 ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+              o[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]) + bia.x,
+                                 __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]) + bia.y,
+                                 __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]) + bia.z,
+                                 __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]) + bia.w);
+            }
+          }
+          if (c.act == YL_ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o[j].x = fmaxf(o[j].x, 0.f); o[j].y = fmaxf(o[j].y, 0.f); o[j].z = fmaxf(o[j].z, 0.f); o[j].w = fmaxf(o[j].w, 0.f); }
+          } else if (c.act) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = act4(o[j], c.act);
+          }
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read the staging tile
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sb + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && wvalid) {
+            if (spatial)
+              asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                           ::"l"(&omap), "r"(chunk_n0 + col), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(sb)) : "memory");
+            else
+              asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];"
+                           ::"l"(&omap), "r"(chunk_n0 + col), "r"(c1), "r"(smem_u32(sb)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        if (p.epi2) acc_phase ^= 1;
+        else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       // element offset of the output row for each of the 8 rows this lane owns, -1 = outside
       int orow[8];
       if (spatial) {
@@ -1108,6 +1186,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       if (p.epi2) acc_phase ^= 1;                              // this group owns one accumulator
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores are complete
   }
 
   // ---- teardown
@@ -1141,7 +1220,8 @@ static void tc_pick_tile(int ks, int stride, int Hout, int Wout, TcPlan* pl) {
     const int hp = hw_ * hh_;
     if (hp * 128 > 48 * 1024 || hw_ > 256 || hh_ > 256) continue;   // keep a ring of >= 2 slots affordable
     const long long ntile = (long long)((Wout + tw - 1) / tw) * ((Hout + th - 1) / th);
-    const long long cost = ntile * (hp + 128);
+    long long cost = ntile * (hp + 128);
+    if (32 % tw != 0) cost += cost * 15 / 100;                  // tile widths dividing 32 can use the TMA-store epilogue
     if (best < 0 || cost < best) { best = cost; pl->tile_w = tw; pl->tile_h = th; pl->halo_w = hw_; pl->halo_h = hh_; pl->halo_pix = hp; }
   }
   pl->halo_bytes = pl->halo_pix * 128;
@@ -1175,7 +1255,7 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
     const size_t wbytes = (size_t)2 * nslab * Nc * 128;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
-    size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
+    size_t fixed = wbytes + (mode == 3 ? TC_AUX_BYTES - 4 * (TC_STG_BYTES - 4608) : TC_AUX_BYTES) + dense_bytes + 1024;
     pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 0; pl->halo_slots = 0;
     if (mode == 3) {                             // stem-output halo + input patch, 2 A stages
       fixed += (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES + 2 * 2 * TC_SLAB_BYTES;
@@ -1196,7 +1276,7 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
     }
     if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
     // second epilogue group (MODE 0 + TMA, plain vector epilogue): four more transpose staging buffers, if 3 stages still fit
-    const size_t epi2_bytes = (size_t)4 * 32 * TC_EPI_PITCH * 4;
+    const size_t epi2_bytes = (size_t)4 * TC_STG_BYTES;
     pl->epi2 = 0;
     if (want_epi2 && mode == 0 && dense_bytes == 0 && (N & 3) == 0 && anchors <= 1 &&
         fixed + epi2_bytes + 3 * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) {
@@ -1318,6 +1398,7 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
   p.tile_w = pl.tile_w; p.tile_h = pl.tile_h; p.halo_w = pl.halo_w; p.halo_pix = pl.halo_pix; p.halo_bytes = pl.halo_bytes;
   p.dw_stride = mode == 2 ? c.stride : 1;
+  p.stg_stride = mode == 3 ? 4608 : TC_STG_BYTES;
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE((c.Cin & 3) == 0, "tcgen05 conv needs Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
@@ -1396,11 +1477,34 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
     YL_REQUIRE((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && pl.halo_w <= 256 && pl.halo_h <= 256, "halo tile does not fit a TMA box");
     if (int rc = make_halo_tmap(&tmap, c.in, c.B, c.Hin, c.Win, c.Cin, pl.halo_w, pl.halo_h)) return rc;
   }
-  if (mode == 0) tc_conv_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
-  else if (mode == 1) tc_conv_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
-  else if (mode == 2 && c.KS == 3) tc_conv_kernel<2, 3><<<grid, TC_THREADS, smem, st>>>(p, tmap);
-  else if (mode == 2) tc_conv_kernel<2, 5><<<grid, TC_THREADS, smem, st>>>(p, tmap);
-  else tc_conv_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap);
+  // output tensor map for the TMA-store epilogue: plain vector epilogue (N % 4 == 0, no head layout), no residual / upsample
+  // source, every 32-column block inside this CTA's chunk, and in the spatial modes a tile width that divides 32
+  CUtensorMap omap;
+  memset(&omap, 0, sizeof(omap));
+  static const int tmaout_env = [] { const char* e = getenv("YL_TC_TMAOUT"); return e ? atoi(e) : 1; }();
+  const bool spatial = mode == 2 || (mode == 1 && p.tma_a);
+  if (tmaout_env && mode != 3 && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && !c.up && c.Cout >= 32 &&
+      (p.nchunks == 1 || (p.Nc & 31) == 0) && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (!spatial || 32 % p.tile_w == 0)) {
+    int rc;
+    if (spatial) {
+      const unsigned long long dims[4] = {(unsigned long long)c.Cout, (unsigned long long)c.Wout, (unsigned long long)c.Hout, (unsigned long long)c.B};
+      const unsigned long long strides[3] = {(unsigned long long)c.Cout * 4, (unsigned long long)c.Wout * c.Cout * 4, (unsigned long long)c.Hout * c.Wout * c.Cout * 4};
+      const unsigned int box[4] = {32, (unsigned)p.tile_w, (unsigned)(32 / p.tile_w), 1};
+      rc = make_tmap_f32(&omap, c.out, 4, dims, strides, box, true);
+    } else {
+      const unsigned long long dims[2] = {(unsigned long long)c.Cout, (unsigned long long)p.M};
+      const unsigned long long strides[1] = {(unsigned long long)c.Cout * 4};
+      const unsigned int box[2] = {32, 32};
+      rc = make_tmap_f32(&omap, c.out, 2, dims, strides, box, true);
+    }
+    if (rc) return rc;
+    p.tma_out = 1;
+  }
+  if (mode == 0) tc_conv_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
+  else if (mode == 1) tc_conv_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
+  else if (mode == 2 && c.KS == 3) tc_conv_kernel<2, 3><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
+  else if (mode == 2) tc_conv_kernel<2, 5><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
+  else tc_conv_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
