@@ -938,11 +938,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           c1 = (rem % p.tiles_x) * p.tile_w; c2 = (rem / p.tiles_x) * p.tile_h + q * rpw; c3 = b;
           wvalid = q * rpw < p.tile_h && c2 < c.Hout;
         }
+        // nearest-upsampled coarser level (FPN laterals, linear tiles): this lane's row reads 32 consecutive channels of its source
+        // pixel; the loads are issued before the accumulator is read so that their latency overlaps it
+        const float* up_row = nullptr;
+        if (MODE == 0 && c.up) {
+          const int m = min(mw + lane, M - 1);
+          const int b = m / hw, rem = m - b * hw;
+          const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
+          up_row = c.up + ((size_t)(b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N + chunk_n0;
+        }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
         for (int col = 0; col < p.Nc; col += 32) {
           float4 o[8];
+          if (MODE == 0 && c.up) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = chunk_n0 + col + 4 * j < N ? __ldg(reinterpret_cast<const float4*>(up_row + col + 4 * j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           {
             uint32_t v[32], w[32];
             if (p.Nc - col > 16) {
@@ -959,10 +976,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 bia = col + 4 * j < 128 ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              o[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]) + bia.x,
-                                 __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]) + bia.y,
-                                 __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]) + bia.z,
-                                 __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]) + bia.w);
+              o[j].x += __uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]) + bia.x;
+              o[j].y += __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]) + bia.y;
+              o[j].z += __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]) + bia.z;
+              o[j].w += __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]) + bia.w;
             }
           }
           if (c.act == YL_ACT_RELU) {
@@ -1483,7 +1500,7 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   memset(&omap, 0, sizeof(omap));
   static const int tmaout_env = [] { const char* e = getenv("YL_TC_TMAOUT"); return e ? atoi(e) : 1; }();
   const bool spatial = mode == 2 || (mode == 1 && p.tma_a);
-  if (tmaout_env && mode != 3 && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && !c.up && c.Cout >= 32 &&
+  if (tmaout_env && mode != 3 && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && (!c.up || (mode == 0 && (reinterpret_cast<uintptr_t>(c.up) & 15) == 0)) && c.Cout >= 32 &&
       (p.nchunks == 1 || (p.Nc & 31) == 0) && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (!spatial || 32 % p.tile_w == 0)) {
     int rc;
     if (spatial) {
