@@ -227,9 +227,9 @@ def run_b200(a):
         gcounts = torch.empty((world * B,), device=dev, dtype=torch.int32)
     extra_launches = 0
 
-    def step(xin):
+    def step(xin, pp=None):
         eng.forward(xin, out=outs)
-        d = post(outs, S, a.conf, a.iou, a.max_det, cap=a.cap)
+        d = (pp or post)(outs, S, a.conf, a.iou, a.max_det, cap=a.cap)
         if world > 1:      # the path's one exchange: gather the fixed-capacity detections
             ydist.pack_detections(d.boxes, d.scores, d.classes, out=packed)
             ydist.gather_detections(packed, d.counts, out=gathered, out_counts=gcounts)
@@ -353,17 +353,25 @@ def run_b200(a):
         hs = torch.empty((B, a.cap)).pin_memory()
         hc = torch.empty((B, a.cap), dtype=torch.int64).pin_memory()
         hn = torch.empty((B,), dtype=torch.int32).pin_memory()
-        s_copy, s_comp = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        s_copy, s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         copied = [torch.cuda.Event(), torch.cuda.Event()]
         freed = [torch.cuda.Event(), torch.cuda.Event()]
-        xpre = torch.empty_like(x)
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        xpre = [torch.empty_like(x), torch.empty_like(x)]
+        posts = [y.PostProcessor(), y.PostProcessor()]      # detection buffers double-buffered against the output stage
+
+        sep_out = os.environ.get("YL_BENCH_SEP_OUT", "0") != "0"      # D2H on its own stream measured slower (A/B on one box)
 
         def e2e_run(k, host, devbuf, from_u8):
+            """Three-stage pipeline over CUDA streams, every step: (copy stream) H2D of the step's pinned host input; (compute
+            stream) letterbox/normalise kernel for images, forward, postprocess; (output stream) D2H of the detections into
+            pinned host buffers.  Step i+1's H2D and step i-1's D2H overlap step i's compute."""
             st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             if world > 1:
                 dist.barrier()
             st.record(s_copy)
+            keep = [None, None]
             for i in range(k):
                 j = i & 1
                 with torch.cuda.stream(s_copy):
@@ -373,14 +381,22 @@ def run_b200(a):
                     copied[j].record(s_copy)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(copied[j])
+                    if i >= 2:
+                        s_comp.wait_event(done[j])          # the D2H of step i-2 has read its detection buffers' slot
                     if from_u8:      # uint8 HWC BGR -> letterbox(identity at 640) + RGB + normalise + CHW on the GPU
-                        xin, _ = y.preprocess_batch(devbuf[j], S, out=xpre)
+                        xin, _ = y.preprocess_batch(devbuf[j], S, out=xpre[j])
                     else:
                         xin = devbuf[j]
-                    dd = step(xin)
+                    dd = step(xin, posts[j])
+                    freed[j].record(s_comp)
+                with torch.cuda.stream(s_out if sep_out else s_comp):
+                    if sep_out:
+                        s_out.wait_event(freed[j])
                     hb.copy_(dd.boxes, non_blocking=True); hs.copy_(dd.scores, non_blocking=True)
                     hc.copy_(dd.classes, non_blocking=True); hn.copy_(dd.counts, non_blocking=True)
-                    freed[j].record(s_comp)
+                    done[j].record(s_out if sep_out else s_comp)
+                    keep[j] = dd                             # keep the device results alive until their copy has been issued twice over
+            s_comp.wait_stream(s_out)
             en.record(s_comp)
             torch.cuda.synchronize(dev)
             ms_e = st.elapsed_time(en)
@@ -398,7 +414,8 @@ def run_b200(a):
         e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(u8h.numel()),
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / a.steps,
                "api": "preprocess_batch(uint8 HWC BGR) + YoloLiteB200.forward + PostProcessor (= YoloLite.predict_batch) on pinned "
-                      "host images; H2D double-buffered on a copy stream; includes the GPU letterbox/normalise kernel"}
+                      "host images; stream pipeline (H2D of step i+1 on a copy stream | GPU letterbox/normalise + forward + postprocess + D2H of the detections), every "
+                      "stage runs every step inside the timed region"}
         xh = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()
         xh.copy_(x.cpu())
         xd = [torch.empty_like(x), torch.empty_like(x)]
