@@ -360,6 +360,7 @@ def run_b200(a):
         xpre = [torch.empty_like(x), torch.empty_like(x)]
         posts = [y.PostProcessor(), y.PostProcessor()]      # detection buffers double-buffered against the output stage
 
+        u8_direct = eng.supports_u8(S, S) and os.environ.get("YL_BENCH_U8_DIRECT", "1") != "0"
         sep_out = os.environ.get("YL_BENCH_SEP_OUT", "0") != "0"      # D2H on its own stream measured slower (A/B on one box)
 
         def e2e_run(k, host, devbuf, from_u8):
@@ -383,11 +384,20 @@ def run_b200(a):
                     s_comp.wait_event(copied[j])
                     if i >= 2:
                         s_comp.wait_event(done[j])          # the D2H of step i-2 has read its detection buffers' slot
-                    if from_u8:      # uint8 HWC BGR -> letterbox(identity at 640) + RGB + normalise + CHW on the GPU
-                        xin, _ = y.preprocess_batch(devbuf[j], S, out=xpre[j])
+                    if from_u8 and u8_direct:
+                        # 640x640 images need no letterbox resize: the stem kernel reads the uint8 BGR batch itself (BGR->RGB,
+                        # /255, (x-mean)/std folded into its weights) -- the path YoloLite.predict_batch takes
+                        eng.forward_u8(devbuf[j], out=outs)
+                        dd = posts[j](outs, S, a.conf, a.iou, a.max_det, cap=a.cap)
+                        if world > 1:
+                            ydist.pack_detections(dd.boxes, dd.scores, dd.classes, out=packed)
+                            ydist.gather_detections(packed, dd.counts, out=gathered, out_counts=gcounts)
                     else:
-                        xin = devbuf[j]
-                    dd = step(xin, posts[j])
+                        if from_u8:      # uint8 HWC BGR -> letterbox + RGB + normalise + CHW on the GPU
+                            xin, _ = y.preprocess_batch(devbuf[j], S, out=xpre[j])
+                        else:
+                            xin = devbuf[j]
+                        dd = step(xin, posts[j])
                     freed[j].record(s_comp)
                 with torch.cuda.stream(s_out if sep_out else s_comp):
                     if sep_out:
@@ -413,7 +423,8 @@ def run_b200(a):
         ms_e = e2e_run(a.steps, u8h, u8d, True)
         e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(u8h.numel()),
                "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / a.steps,
-               "api": "preprocess_batch(uint8 HWC BGR) + YoloLiteB200.forward + PostProcessor (= YoloLite.predict_batch) on pinned "
+               "api": ("YoloLiteB200.forward_u8(uint8 HWC BGR; normalisation folded into the stem kernel)" if u8_direct else
+                       "preprocess_batch(uint8 HWC BGR) + YoloLiteB200.forward") + " + PostProcessor (= YoloLite.predict_batch) on pinned "
                       "host images; stream pipeline (H2D of step i+1 on a copy stream | GPU letterbox/normalise + forward + postprocess + D2H of the detections), every "
                       "stage runs every step inside the timed region"}
         xh = torch.empty((B, 3, S, S), dtype=torch.float32).pin_memory()

@@ -69,7 +69,9 @@ typedef struct yl_op {
                         into TF32 hi/lo and pre-swizzled (SWIZZLE_128B, K-major), or -1 */
   int64_t w3_off;    /* YL_OP_STEM2: float offset of the bf16-triple weight image of the fused stem kernel
                         ([9 taps][3 splits][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
-                        row 64 B, SWIZZLE_64B K-major, two bf16 per float slot), or -1 (older tf32 kernel) */
+                        row 64 B, SWIZZLE_64B K-major, two bf16 per float slot; followed by a second [3 splits][32][32] stem image
+                        for uint8 input with 1/(255 std) and the -mean/std terms folded in: rows k = 27..30 = constant, top-border,
+                        left-border and top-left-corner terms), or -1 (older tf32 kernel) */
   int64_t b2_off;    /* YL_OP_DWPW: float offset of the depthwise bias (cin floats, folded BN), or -1.
                         YL_OP_STEM2: float offset of a fused pointwise conv applied after the second conv (timm blocks.0.1):
                         [cout][cout] weights (k-major, BN folded) followed by cout biases, cout = 16 only; or -1 */
@@ -98,6 +100,14 @@ int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shape
  * allocated [B,A,S,S,5+C] fp32 contiguous, channel order (tx,ty,tw,th,obj,cls0..).  x is not modified.  */
 int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
                void* stream);
+
+/* model(x) on an image batch that needs no letterbox resize: images_bgr is [B,H,W,3] uint8 BGR on the device (what
+ * cv2.imread gives the reference, tools/infer.py:436), H = W = the network input size.  Equivalent to yl_preprocess_batch
+ * (BGR->RGB, /255, (x-mean)/std, CHW; tools/infer.py:442-453) followed by yl_forward, but the normalisation is folded into the
+ * stem weights (it is affine in the integer pixel value) and the fp32 image never exists in HBM.  Needs the fused stem op
+ * (YL_OP_STEM2 with w3_off), even H and W % 16 == 0; returns -1 otherwise (callers fall back to yl_preprocess_batch + yl_forward). */
+int yl_forward_u8(yl_engine* e, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, float* const* level_out,
+                  void* stream);
 
 /* Same as yl_forward but brackets every op with CUDA events on `stream` and returns the device time of each
  * op in milliseconds (op_ms[n_ops]); synchronises the stream.  Used by bench.py for the per-kernel roofline. */

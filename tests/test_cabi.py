@@ -12,7 +12,7 @@ from conftest import REPO
 def _declared():
     with open(os.path.join(REPO, "include", "yololite_b200.h")) as f:
         src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
-    return sorted(set(re.findall(r"\b(yl_[a-z_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(yl_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():

@@ -9,6 +9,32 @@ from conftest import FWD_CASES, case_ckpt, golden, synth_ckpt
 from oracle import model_ref
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("model,nc,S", [("edge_n", 3, 64), ("edge_n", 80, 320), ("edge_n", 5, 96)])
+def test_forward_u8_matches_preprocess_plus_forward(model, nc, S):
+    """yl_forward_u8 (normalisation folded into the fused stem kernel, one bf16 split for the integer pixels) against
+    yl_preprocess_batch + yl_forward on the same uint8 BGR images, and against the CPU oracle on the normalised tensor."""
+    import yololite_b200 as y
+    from conftest import synth_ckpt
+    from oracle import model_ref, pre_ref
+    ck = synth_ckpt(model, nc, S)
+    eng = y.YoloLiteB200(ck["state_dict"], ck["meta"], device="cuda:0")
+    assert eng.supports_u8(S, S)
+    rs = np.random.RandomState(S + nc)
+    img = rs.randint(0, 256, (3, S, S, 3)).astype(np.uint8)
+    img[0, :2] = 0; img[1, :, :3] = 255; img[2, -2:, -2:] = 0          # exercise the padded borders with extreme values
+    d = torch.from_numpy(img).cuda()
+    x, _ = y.preprocess_batch(d, S)
+    want = eng(x)
+    got = eng.forward_u8(d)
+    xo = torch.from_numpy(np.concatenate([pre_ref.preprocess_ref(im, S)[0] for im in img]))
+    ref = model_ref.forward_ref(ck["state_dict"], ck["meta"], xo)
+    for g, w, r in zip(got, want, ref):
+        assert g.shape == w.shape
+        assert float((g - w).abs().max()) <= 2e-4          # same engine, two input paths
+        assert float((g.cpu() - r).abs().max()) <= 1e-3    # the parity gate against the reference forward
+
 LOGIT_TOL = 1e-3
 
 

@@ -39,6 +39,7 @@ _SIGNATURES = {
                                  ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P]),
     "yl_engine_plan": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32)]),
     "yl_forward": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P]),
+    "yl_forward_u8": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P]),
     "yl_forward_profile": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(_P), _P,
                                           ctypes.POINTER(ctypes.c_float), ctypes.c_int32]),
     "yl_engine_read_buffer": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.POINTER(ctypes.c_int32), _P]),

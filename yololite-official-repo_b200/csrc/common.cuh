@@ -57,6 +57,7 @@ __device__ __forceinline__ int nearest_src(int dst, int in_size, int out_size) {
 
 struct ConvParams {
   const float* __restrict__ in;     // NHWC (or NCHW for the stem)
+  const unsigned char* __restrict__ in_u8;   // YL_OP_STEM2 image mode: [B,H,W,3] uint8 BGR instead of `in`
   const float* __restrict__ w;      // [K][N], k = (ky*KS + kx)*Cin + ci
   const float* __restrict__ bias;   // [N] or nullptr
   const float* __restrict__ res;    // [M][N] or nullptr
@@ -76,6 +77,8 @@ struct ConvParams {
 // out-of-bounds elements read as zero.  cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link).
 int make_tmap_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
                   const unsigned int* box, bool swizzle128);
+int make_tmap_u8(CUtensorMap* tm, const unsigned char* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
+                 const unsigned int* box);
 
 // launchers (conv_kernels.cu)
 int launch_stem(const ConvParams& p, cudaStream_t s);

@@ -45,9 +45,11 @@ bool stem2_supported(const ConvParams& c);
 int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st);
 
 static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
-                  int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st) {
+                  int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st,
+                  const unsigned char* in_u8 = nullptr) {
   ConvParams p{};
   p.in = in;
+  p.in_u8 = in_u8;
   p.w = blob + op.w_off;
   p.bias = op.b_off >= 0 ? blob + op.b_off : nullptr;
   p.res = res; p.up = up;
@@ -70,6 +72,7 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
     ++g_tc_launches;
     static const int old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
     if (op.w3_off >= 0 && !old_stem && stem2_supported(p)) return launch_stem2(p, blob + op.w3_off, sm_count, st);
+    YL_REQUIRE(!in_u8, "uint8 image input needs the fused bf16 stem kernel (16/32-channel second conv, even H, W % 16 == 0)");
     YL_REQUIRE(!p.b2, "YL_OP_STEM2 with a fused pointwise conv needs the bf16-triple kernel (w3_off, 16 channels, W % 4 == 0)");
     return launch_tc_conv(p, blob + op.wt_off, 3, sm_count, st);
   }
@@ -267,9 +270,11 @@ int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shape
 }
 
 static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
-                        void* stream, cudaEvent_t* ev) {
+                        void* stream, cudaEvent_t* ev, const unsigned char* x_u8 = nullptr) {
   using namespace yl;
-  YL_REQUIRE(e && x && level_out, "null argument");
+  YL_REQUIRE(e && (x || x_u8) && level_out, "null argument");
+  YL_REQUIRE(!x_u8 || (e->ops[0].kind == YL_OP_STEM2 && e->ops[0].src == YL_SRC_INPUT && e->ops[0].w3_off >= 0 && e->use_tc),
+             "this layer program has no uint8 image entry (fused stem kernel required)");
   YL_CHECK_CUDA(cudaSetDevice(e->device));
   if (int rc = plan(e, B, H, W)) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -286,7 +291,7 @@ static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int3
     }
     int rc = run_op(op, e->d_blob, in, op.res >= 0 ? bufptr(op.res) : nullptr, op.up >= 0 ? bufptr(op.up) : nullptr, outp, B,
                     e->op_hin[i], e->op_win[i], e->op_hout[i], e->op_wout[i], e->op_hu[i], e->op_wu[i], e->use_tc,
-                    e->sm_count, st);
+                    e->sm_count, st, op.src == YL_SRC_INPUT ? x_u8 : nullptr);
     if (rc) return rc;
     if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
   }
@@ -295,6 +300,10 @@ static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int3
 
 int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out, void* stream) {
   return forward_impl(e, x, B, H, W, level_out, stream, nullptr);
+}
+
+int yl_forward_u8(yl_engine* e, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, float* const* level_out, void* stream) {
+  return forward_impl(e, nullptr, B, H, W, level_out, stream, nullptr, images_bgr);
 }
 
 int yl_forward_profile(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,

@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -40,6 +41,7 @@ constexpr int S2_PLANE_BYTES = (S2_HPIX * 64 + 511) / 512 * 512;   // one bf16 s
                                                                    // the 512 B swizzle period so all three splits share one XOR pattern
 constexpr int S2_A1_SPLIT = 128 * 64, S2_A1_STAGE = 3 * S2_A1_SPLIT;
 constexpr int S2_PATCH_BYTES = 3 * S2_PR * S2_PP * 4;      // 28944
+constexpr int S2_U8_PITCH = 128;                           // image mode: bytes per patch row (36 pixels x 3 = 108, padded to a 16 B multiple)
 constexpr int S2_WST_BYTES = 3 * 32 * 64;                  // stem weights, three splits
 constexpr int S2_ACC1_RING = 3;                            // stem accumulator ring: 3 x [main 32 | corr 32 | corr 32] TMEM columns
 constexpr uint32_t S2_ACC1_COLS = 96, S2_ACC2_COL = S2_ACC1_RING * S2_ACC1_COLS, S2_ACC2_COLS = 96;   // conv2: 2 x 3*N2 (<= 96)
@@ -53,6 +55,9 @@ struct Stem2Params {
   float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
   int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
   int tiles_x, tiles_y, num_tiles;
+  const unsigned char* __restrict__ in_u8;   // image mode: [B,H,W,3] uint8 BGR (the reference's cv2 image, tools/infer.py:436-453) read
+                                       // directly: (u/255 - mean)/std is affine in the integer u, so it is folded into the stem
+                                       // weights; u8 values are exact in ONE bf16 -> GEMM1 takes one instruction per k-step
   const float* __restrict__ pw;        // optional fused pointwise conv after conv2 (timm blocks.0.1): [Cout][Cout] weights (k-major,
                                        // BN folded) followed by Cout biases; needs Cout == N2 == 16.  nullptr: none
   int pw_act;
@@ -165,9 +170,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   {   // resident weight images, copied verbatim (pre-split, pre-swizzled on the host)
-    const int total4 = (w2_bytes + S2_WST_BYTES) >> 4;
+    const int w24 = w2_bytes >> 4, total4 = (w2_bytes + S2_WST_BYTES) >> 4;
+    const int stem_skip = p.in_u8 ? (S2_WST_BYTES >> 4) : 0;      // image mode: the second stem image (weights folded with 1/(255 std), -mean/std)
     for (int i = threadIdx.x; i < total4; i += S2_THREADS)
-      reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(p.wimg) + i);
+      reinterpret_cast<float4*>(smem)[i] = __ldg(reinterpret_cast<const float4*>(p.wimg) + (i < w24 ? i : i + stem_skip));
   }
   if (has_pw)
     for (int i = threadIdx.x; i < 16 * 16 + 16; i += S2_THREADS) pws[i] = __ldg(p.pw + i);
@@ -193,6 +199,27 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     }
     // the 3 x 67 x 36 input patch (NCHW, zero outside the image = the stem's padding) is ONE TMA box over [B*3][H][W]
     auto issue_patch = [&](int tile) {
+      if (p.in_u8) {
+        // image mode: the 67-row BGR patch (bytes 96 tx - 16 ... + 128 of each row: 4 bytes of slack, then 36 pixels) by 16-byte
+        // cp.async pieces, zero-filled outside the image; W % 16 == 0 keeps every piece aligned and entirely inside or outside
+        if (tile < tiles) {
+          const int b = tile / per_img, rem = tile - b * per_img;
+          const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+          const int iy0 = 4 * S2_TH * ty - 3, xb0 = 3 * (4 * S2_TW * tx - 4) - 4;   // first row; first byte column (16 B aligned)
+          const unsigned char* img = p.in_u8 + (size_t)b * p.H * p.W * 3;
+          const uint32_t pbase = smem_u32(patch);
+          for (int idx = t; idx < S2_PR * (S2_U8_PITCH / 16); idx += 32 * S2_PROD_WARPS) {
+            const int row = idx >> 3, c16 = idx & 7;
+            const int iy = iy0 + row, xb = xb0 + 16 * c16;
+            const bool ok = iy >= 0 && iy < p.H && xb >= 0 && xb + 15 < p.W * 3;
+            const unsigned char* src = ok ? img + (size_t)iy * p.W * 3 + xb : p.in_u8;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pbase + (uint32_t)(row * S2_U8_PITCH + 16 * c16)), "l"(src),
+                         "r"(ok ? 16u : 0u) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        return;
+      }
       if (t == 0 && tile < tiles) {
         const int b = tile / per_img, rem = tile - b * per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -206,13 +233,56 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     issue_patch(blockIdx.x);
     uint32_t pphase = 0;
     uint32_t n = 0;                                          // running stem-tile counter -> A1 stage / phase
+    // image mode: byte offsets of the 8 k's of a chunk (BGR bytes: channel ci of the RGB tensor is byte 2 - ci); the patch row
+    // starts 4 bytes before pixel ixa.  k = 27: constant 1 (bias + full mean/std term), 28: top-border row, 29: left-border
+    // column, 30: top-left corner (they take back the padded taps' share of the mean/std term), 31: zero
+    // image mode uses a warp-uniform chunk (so that only the warps of chunk 3 handle the constant / border columns):
+    // chunk = warp & 3, rows (lane + 32 * (t >> 7)) and + 64
+    const int ch8 = (t >> 5) & 3, rb8 = (t & 31) + 32 * (t >> 7);
+    int boff8[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = ch8 * 8 + m, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+      boff8[m] = k < 27 ? ky * S2_U8_PITCH + 4 + (kx + 1) * 3 + (2 - ci) : 0;
+    }
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-      mbar_wait(smem_u32(patch_full), pphase);               // this tile's patch has landed
-      pphase ^= 1u;
+      if (p.in_u8) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");       // the patch pieces of every producer have landed
+      } else {
+        mbar_wait(smem_u32(patch_full), pphase);             // this tile's patch has landed
+        pphase ^= 1u;
+      }
+      const int trem = tile % per_img;
+      const int sy0 = 2 * S2_TH * (trem / p.tiles_x) - 1, sx0 = 2 * S2_TW * (trem % p.tiles_x) - 1;   // stem-output coords of halo (0,0)
       for (int j = 0; j < S2_MT; ++j, ++n) {
         const uint32_t stage = n & 1u;
         mbar_wait(smem_u32(&a1_empty[stage]), ((n >> 1) & 1u) ^ 1u);
         unsigned char* st = a1 + stage * S2_A1_STAGE;
+        if (p.in_u8) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int r = rb8 + 64 * i, q = j * 128 + r;
+            if (q < S2_HPIX) {
+              const int hy = q / S2_HW, hx = q - hy * S2_HW;
+              const unsigned char* pb = reinterpret_cast<const unsigned char*>(patch) + 2 * hy * S2_U8_PITCH + 6 * hx;
+              float e[8];
+#pragma unroll
+              for (int m = 0; m < 8; ++m) e[m] = (float)pb[boff8[m]];
+              if (ch8 == 3) {                                  // k = 24..26 are taps; 27: 1, 28: top row, 29: left column, 30: corner
+                const float top = (sy0 + hy == 0) ? 1.f : 0.f, left = (sx0 + hx == 0) ? 1.f : 0.f;
+                e[3] = 1.f; e[4] = top; e[5] = left; e[6] = top * left; e[7] = 0.f;
+              }
+              uint4 o1;                                       // integers 0..255 are exact in bf16
+              __nv_bfloat162 h;
+              h = __floats2bfloat162_rn(e[0], e[1]); o1.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(e[2], e[3]); o1.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(e[4], e[5]); o1.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2bfloat162_rn(e[6], e[7]); o1.w = *reinterpret_cast<uint32_t*>(&h);
+              *reinterpret_cast<uint4*>(st + (uint32_t)r * 64u + (uint32_t)((ch8 ^ ((r >> 1) & 3)) << 4)) = o1;
+            }
+          }
+        } else
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
           const int r = r0 + 64 * i, q = j * 128 + r;
@@ -264,8 +334,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t db = dWs + (uint64_t)((ks * 32) >> 4);
             mma_bf16(d0, da0 + (uint64_t)((0 * S2_A1_SPLIT + ks * 32) >> 4), db, i1a, ks > 0);        // A1 x [W1|W2|W3]
-            mma_bf16(d0 + 32u, da0 + (uint64_t)((1 * S2_A1_SPLIT + ks * 32) >> 4), db, i1b, 1u);      // A2 x [W1|W2]
-            mma_bf16(d0 + 64u, da0 + (uint64_t)((2 * S2_A1_SPLIT + ks * 32) >> 4), db, i1c, 1u);      // A3 x [W1]
+            if (!p.in_u8) {                                                                           // image mode: A = A1 exactly
+              mma_bf16(d0 + 32u, da0 + (uint64_t)((1 * S2_A1_SPLIT + ks * 32) >> 4), db, i1b, 1u);    // A2 x [W1|W2]
+              mma_bf16(d0 + 64u, da0 + (uint64_t)((2 * S2_A1_SPLIT + ks * 32) >> 4), db, i1c, 1u);    // A3 x [W1]
+            }
           }
           mma_commit(smem_u32(&a1_empty[stage]));
           mma_commit(smem_u32(&acc1_full[slot]));
@@ -477,15 +549,17 @@ static size_t stem2_smem_bytes(int N2) {
 
 bool stem2_supported(const ConvParams& c) {
   const int N2 = (c.Cout + 15) / 16 * 16;
-  return c.KS == 3 && c.stride == 2 && c.Cin == 32 && (c.Cout & 3) == 0 && N2 <= 32 && (c.Win & 3) == 0 &&
-         (reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && stem2_smem_bytes(N2) <= (size_t)227 * 1024 && !c.res && !c.up &&
+  // image mode: the folded-normalisation border terms cover the top / left padding only (even H, W: no bottom / right padding)
+  const bool in_ok = c.in_u8 ? ((reinterpret_cast<uintptr_t>(c.in_u8) & 15) == 0 && (c.Hin & 1) == 0 && (c.Win & 15) == 0)
+                             : ((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && (c.Win & 3) == 0);
+  return c.KS == 3 && c.stride == 2 && c.Cin == 32 && (c.Cout & 3) == 0 && N2 <= 32 && in_ok && stem2_smem_bytes(N2) <= (size_t)227 * 1024 && !c.res && !c.up &&
          c.anchors <= 1 && c.bias != nullptr;
 }
 
 // c: geometry of the SECOND conv as set up by engine.cu for YL_OP_STEM2 (Hin/Win = network input size, Hout/Wout = conv2 output)
 int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st) {
   Stem2Params p{};
-  p.in = c.in; p.wimg = wimg; p.bias2 = c.bias; p.out = c.out;
+  p.in = c.in; p.in_u8 = c.in_u8; p.wimg = wimg; p.bias2 = c.bias; p.out = c.out;
   p.B = c.B; p.H = c.Hin; p.W = c.Win;
   p.Hs = (c.Hin + 2 - 3) / 2 + 1; p.Ws = (c.Win + 2 - 3) / 2 + 1;
   p.Ho = c.Hout; p.Wo = c.Wout; p.Cout = c.Cout; p.N2 = (c.Cout + 15) / 16 * 16; p.act = c.act;
@@ -505,7 +579,8 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
   }
   int gx = sm_count < p.num_tiles ? sm_count : p.num_tiles;
   CUtensorMap tmap;
-  {
+  memset(&tmap, 0, sizeof(tmap));
+  if (!p.in_u8) {
     const unsigned long long dims[3] = {(unsigned long long)p.W, (unsigned long long)p.H, (unsigned long long)p.B * 3};
     const unsigned long long strides[2] = {(unsigned long long)p.W * 4, (unsigned long long)p.H * p.W * 4};
     const unsigned int box[3] = {(unsigned)S2_PP, (unsigned)S2_PR, 3};

@@ -95,6 +95,29 @@ class YoloLiteB200:
 
     __call__ = forward
 
+    def forward_u8(self, images: torch.Tensor, out: Optional[Sequence[torch.Tensor]] = None):
+        """model(normalise(images)) for a CUDA uint8 batch [B,S,S,3] in BGR (cv2 order) that needs no letterbox resize:
+        BGR->RGB, /255, (x-mean)/std (tools/infer.py:442-453) are folded into the stem kernel, the fp32 image never
+        exists.  Raises ValueError when the engine / shape has no uint8 entry (use preprocess_batch + forward then)."""
+        if not (isinstance(images, torch.Tensor) and images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4
+                and images.shape[3] == 3):
+            raise ValueError("expected a CUDA uint8 tensor of shape [B,H,W,3] (BGR)")
+        images = images.contiguous()
+        B, H, W, _ = images.shape
+        shapes = self.level_shapes(B, H, W)
+        if out is None:
+            out = [torch.empty((B, A, sh, sw, D), device=images.device, dtype=torch.float32) for (A, sh, sw, D) in shapes]
+        ptrs = (ctypes.c_void_p * self._n_levels)(*[o.data_ptr() for o in out])
+        L.check(L.lib().yl_forward_u8(self._h, ctypes.c_void_p(images.data_ptr()), B, H, W, ptrs, _stream_ptr(images.device)))
+        out = list(out)
+        if self.export_concat:
+            return torch.cat([o.view(B, -1, o.shape[-1]) for o in out], dim=1)
+        return out
+
+    def supports_u8(self, H: int, W: int) -> bool:
+        op0 = self.program.ops[0]
+        return bool(op0["kind"] == L.OP_STEM2 and op0["w3_off"] >= 0 and H % 2 == 0 and W % 16 == 0)
+
     def profile_ops(self, x: torch.Tensor):
         """Per-op device milliseconds of one forward (CUDA events between launches) -> list of (op dict, ms)."""
         x = x.contiguous()

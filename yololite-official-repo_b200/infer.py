@@ -134,6 +134,10 @@ class YoloLite:
         """Batched device-side predict: uint8 [B,H,W,3] BGR (CUDA) -> Detections (fixed capacity, letterboxed coordinates)
         + the letterbox geometry.  No host synchronisation; call `.to_list()` / `backmap` on the result when needed."""
         S = int(img_size) if img_size else self.img_size
+        B, h0, w0 = images_u8.shape[0], images_u8.shape[1], images_u8.shape[2]
+        if h0 == S and w0 == S and self.model.supports_u8(S, S):
+            # no letterbox resize / padding needed: the stem kernel reads the uint8 image itself (normalisation folded in)
+            return self._post(self.model.forward_u8(images_u8), S, conf, iou, max_det, cap), (1.0, 0, 0, h0, w0)
         key = (tuple(images_u8.shape), S)
         if getattr(self, "_xbuf_key", None) != key:
             self._xbuf = torch.empty((images_u8.shape[0], 3, S, S), device=images_u8.device, dtype=torch.float32)

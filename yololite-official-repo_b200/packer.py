@@ -193,6 +193,25 @@ def bf16_split3(x: np.ndarray):
     return b1, b2, b3
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)      # tools/infer.py:432-433
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+def bf16_split3_f64(x: np.ndarray):
+    """float64 x -> three bf16 bit patterns with x ~= b1 + b2 + b3 (24 bits kept): like bf16_split3 but the residuals are
+    taken in float64, so nothing is lost to an intermediate fp32 rounding."""
+    def rn(v):
+        f = np.asarray(v, np.float64).astype(np.float32)
+        u = f.view(np.uint32).astype(np.uint64)
+        r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint32)
+        return r.astype(np.uint16), (r << 16).astype(np.uint32).view(np.float32).astype(np.float64)
+    x = np.asarray(x, np.float64)
+    b1, f1 = rn(x)
+    b2, f2 = rn(x - f1)
+    b3, _ = rn(x - f1 - f2)
+    return b1, b2, b3
+
+
 def _sw64_rows(m: np.ndarray) -> np.ndarray:
     """[rows][32] uint16 -> the K-major SWIZZLE_64B image: row r holds four 16 B chunks, chunk c at position c ^ ((r >> 1) & 3)."""
     rows = m.shape[0]
@@ -222,6 +241,22 @@ def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> 
         for sp in sp2:
             parts.append(_sw64_rows(sp[t]).reshape(-1))
     for sp in bf16_split3(st):
+        parts.append(_sw64_rows(sp).reshape(-1))
+    # second stem image, for uint8 BGR input (yl_forward_u8): x = a_c*u + b_c with a_c = 1/(255 std_c), b_c = -mean_c/std_c
+    # (tools/infer.py:432-433,449-451) is affine in the integer u, so  conv(x) = sum_k (w_k a_c) u_k + sum_{valid k} w_k b_c.
+    # Row 27 (times 1) carries bias + the full b-term; rows 28 / 29 / 30 (times the top-row / left-column / corner
+    # indicators) take back the taps that fall into the zero padding there.  Computed in float64, then split.
+    wsd = np.asarray(ws, np.float64).reshape(3, 3, 3, 32)                 # [ky][kx][ci][n]
+    a = 1.0 / (255.0 * np.asarray(IMAGENET_STD, np.float64))
+    b = -np.asarray(IMAGENET_MEAN, np.float64) / np.asarray(IMAGENET_STD, np.float64)
+    su = np.zeros((32, 32), np.float64)
+    su[:, :27] = (wsd * a[None, None, :, None]).reshape(27, 32).T
+    wb = wsd * b[None, None, :, None]
+    su[:, 27] = np.asarray(b0, np.float64) + wb.sum(axis=(0, 1, 2))
+    su[:, 28] = -wb[0].sum(axis=(0, 1))
+    su[:, 29] = -wb[:, 0].sum(axis=(0, 1))
+    su[:, 30] = wb[0, 0].sum(axis=0)
+    for sp in bf16_split3_f64(su):
         parts.append(_sw64_rows(sp).reshape(-1))
     return np.concatenate(parts).astype(np.uint16).view(np.float32)
 
