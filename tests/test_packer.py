@@ -105,3 +105,31 @@ def test_tc_weight_image_layout():
             assert img[((0 * nslab + s) * npad + n) * 32 + pos] == hi
             assert img[((1 * nslab + s) * npad + n) * 32 + pos] == lo
             assert abs(float(want) - float(hi) - float(lo)) <= abs(float(want)) * 2.0 ** -21
+
+
+def test_stem_u8_matrix_reproduces_normalise_then_conv():
+    """The uint8 entry folds (u/255 - mean)/std into the stem weights (packer.stem_u8_matrix): checked in float64 against
+    normalise -> zero-padded 3x3 s2 conv on an even-sized image, including the top / left border pixels whose padded taps
+    the indicator columns take back."""
+    rs = np.random.RandomState(0)
+    H, W, n = 12, 16, 32
+    w = rs.randn(n, 3, 3, 3)                                   # [n][ci][ky][kx]
+    b0 = rs.randn(n)
+    ws = np.transpose(w, (2, 3, 1, 0)).reshape(27, n)          # k = (ky*3+kx)*3 + ci
+    su = packer.stem_u8_matrix(ws, b0)
+    img = rs.randint(0, 256, (H, W, 3)).astype(np.float64)     # RGB order, integer values
+    mean, std = np.array(packer.IMAGENET_MEAN), np.array(packer.IMAGENET_STD)
+    x = (img / 255.0 - mean) / std
+    want = torch.nn.functional.conv2d(torch.from_numpy(x).permute(2, 0, 1)[None], torch.from_numpy(w), torch.from_numpy(b0),
+                                      stride=2, padding=1)[0].numpy()           # [n][H/2][W/2]
+    pad = np.zeros((H + 2, W + 2, 3))
+    pad[1:-1, 1:-1] = img                                       # raw bytes, zero outside (what the kernel's patch holds)
+    got = np.zeros_like(want)
+    for sy in range(H // 2):
+        for sx in range(W // 2):
+            a = np.zeros(32)
+            a[:27] = pad[2 * sy:2 * sy + 3, 2 * sx:2 * sx + 3, :].reshape(27)
+            a[27], a[28], a[29] = 1.0, float(sy == 0), float(sx == 0)
+            a[30] = a[28] * a[29]
+            got[:, sy, sx] = su @ a
+    assert np.abs(got - want).max() < 1e-10

@@ -223,6 +223,24 @@ def _sw64_rows(m: np.ndarray) -> np.ndarray:
     return out.reshape(rows, 32)
 
 
+def stem_u8_matrix(ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
+    """Stem weights for uint8 input as a float64 [32 out][32 k] matrix.  ws: [27][32] (k = (ky*3+kx)*3 + ci, BN folded),
+    b0: [32].  Columns 0..26 multiply the raw pixel bytes (channel ci of the RGB tensor), 27 a constant 1, 28 / 29 / 30
+    the indicators "stem output row 0" / "column 0" / both (the taps in the zero padding there), 31 is unused."""
+    wsd = np.asarray(ws, np.float64).reshape(3, 3, 3, -1)                 # [ky][kx][ci][n]
+    n = wsd.shape[-1]
+    a = 1.0 / (255.0 * np.asarray(IMAGENET_STD, np.float64))
+    b = -np.asarray(IMAGENET_MEAN, np.float64) / np.asarray(IMAGENET_STD, np.float64)
+    su = np.zeros((n, 32), np.float64)
+    su[:, :27] = (wsd * a[None, None, :, None]).reshape(27, n).T
+    wb = wsd * b[None, None, :, None]
+    su[:, 27] = np.asarray(b0, np.float64) + wb.sum(axis=(0, 1, 2))
+    su[:, 28] = -wb[0].sum(axis=(0, 1))
+    su[:, 29] = -wb[:, 0].sum(axis=(0, 1))
+    su[:, 30] = wb[0, 0].sum(axis=0)
+    return su
+
+
 def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
     """Weight image of the fused stem kernel as float32 words (two bf16 per word, bits preserved):
     [9 taps][3 splits][ceil16(n_out)][32 ch] conv2 weights (the three splits of a tap are adjacent row blocks, so one
@@ -246,16 +264,7 @@ def stem2_image(w2m: np.ndarray, n_out: int, ws: np.ndarray, b0: np.ndarray) -> 
     # (tools/infer.py:432-433,449-451) is affine in the integer u, so  conv(x) = sum_k (w_k a_c) u_k + sum_{valid k} w_k b_c.
     # Row 27 (times 1) carries bias + the full b-term; rows 28 / 29 / 30 (times the top-row / left-column / corner
     # indicators) take back the taps that fall into the zero padding there.  Computed in float64, then split.
-    wsd = np.asarray(ws, np.float64).reshape(3, 3, 3, 32)                 # [ky][kx][ci][n]
-    a = 1.0 / (255.0 * np.asarray(IMAGENET_STD, np.float64))
-    b = -np.asarray(IMAGENET_MEAN, np.float64) / np.asarray(IMAGENET_STD, np.float64)
-    su = np.zeros((32, 32), np.float64)
-    su[:, :27] = (wsd * a[None, None, :, None]).reshape(27, 32).T
-    wb = wsd * b[None, None, :, None]
-    su[:, 27] = np.asarray(b0, np.float64) + wb.sum(axis=(0, 1, 2))
-    su[:, 28] = -wb[0].sum(axis=(0, 1))
-    su[:, 29] = -wb[:, 0].sum(axis=(0, 1))
-    su[:, 30] = wb[0, 0].sum(axis=0)
+    su = stem_u8_matrix(ws, b0)
     for sp in bf16_split3_f64(su):
         parts.append(_sw64_rows(sp).reshape(-1))
     return np.concatenate(parts).astype(np.uint16).view(np.float32)
