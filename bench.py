@@ -203,6 +203,9 @@ def run_b200(a):
     torch.cuda.set_device(dev)
     dist = None
     if world > 1:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B, S = a.batch, a.img
