@@ -364,7 +364,9 @@ def run_b200(a):
         posts = [y.PostProcessor(), y.PostProcessor()]      # detection buffers double-buffered against the output stage
 
         u8_direct = eng.supports_u8(S, S) and os.environ.get("YL_BENCH_U8_DIRECT", "1") != "0"
-        sep_out = os.environ.get("YL_BENCH_SEP_OUT", "0") != "0"      # D2H on its own stream measured slower (A/B on one box)
+        sep_out = os.environ.get("YL_BENCH_SEP_OUT", "0") != "0"
+        dbg_no_h2d = os.environ.get("YL_BENCH_DBG_NO_H2D", "0") == "1"      # diagnostics only: such a run is not an e2e number
+        dbg_no_d2h = os.environ.get("YL_BENCH_DBG_NO_D2H", "0") == "1"      # D2H on its own stream measured slower (A/B on one box)
 
         def e2e_run(k, host, devbuf, from_u8):
             """Three-stage pipeline over CUDA streams, every step: (copy stream) H2D of the step's pinned host input; (compute
@@ -381,7 +383,8 @@ def run_b200(a):
                 with torch.cuda.stream(s_copy):
                     if i >= 2:
                         s_copy.wait_event(freed[j])
-                    devbuf[j].copy_(host, non_blocking=True)
+                    if not dbg_no_h2d:
+                        devbuf[j].copy_(host, non_blocking=True)
                     copied[j].record(s_copy)
                 with torch.cuda.stream(s_comp):
                     s_comp.wait_event(copied[j])
@@ -405,8 +408,9 @@ def run_b200(a):
                 with torch.cuda.stream(s_out if sep_out else s_comp):
                     if sep_out:
                         s_out.wait_event(freed[j])
-                    hb.copy_(dd.boxes, non_blocking=True); hs.copy_(dd.scores, non_blocking=True)
-                    hc.copy_(dd.classes, non_blocking=True); hn.copy_(dd.counts, non_blocking=True)
+                    if not dbg_no_d2h:
+                        hb.copy_(dd.boxes, non_blocking=True); hs.copy_(dd.scores, non_blocking=True)
+                        hc.copy_(dd.classes, non_blocking=True); hn.copy_(dd.counts, non_blocking=True)
                     done[j].record(s_out if sep_out else s_comp)
                     keep[j] = dd                             # keep the device results alive until their copy has been issued twice over
             s_comp.wait_stream(s_out)
@@ -422,6 +426,9 @@ def run_b200(a):
         d2h = int(hb.numel() * 4 + hs.numel() * 4 + hc.numel() * 8 + hn.numel() * 4)
         u8h = synth_input_u8(B, S, 1234 + rank, dev).cpu().pin_memory()
         u8d = [torch.empty((B, S, S, 3), dtype=torch.uint8, device=dev) for _ in range(2)]
+        if dbg_no_h2d:
+            for d_ in u8d:
+                d_.copy_(u8h)
         e2e_run(3, u8h, u8d, True)
         ms_e = e2e_run(a.steps, u8h, u8d, True)
         e2e = {"value": world * B * a.steps / (ms_e / 1e3), "unit": "images/s", "h2d_bytes_per_step": int(u8h.numel()),
