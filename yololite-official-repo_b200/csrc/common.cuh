@@ -77,8 +77,6 @@ struct ConvParams {
 // out-of-bounds elements read as zero.  cuTensorMapEncodeTiled is resolved through the runtime (no libcuda link).
 int make_tmap_f32(CUtensorMap* tm, const float* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
                   const unsigned int* box, bool swizzle128);
-int make_tmap_u8(CUtensorMap* tm, const unsigned char* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
-                 const unsigned int* box);
 
 // launchers (conv_kernels.cu)
 int launch_stem(const ConvParams& p, cudaStream_t s);

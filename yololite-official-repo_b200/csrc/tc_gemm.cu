@@ -1359,21 +1359,6 @@ int make_tmap_f32(CUtensorMap* tm, const float* base, int rank, const unsigned l
   return 0;
 }
 
-int make_tmap_u8(CUtensorMap* tm, const unsigned char* base, int rank, const unsigned long long* dims, const unsigned long long* strides,
-                 const unsigned int* box) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  YL_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
-  YL_REQUIRE(rank >= 1 && rank <= 5, "tensor map rank 1..5");
-  cuuint64_t d[5], st[5];
-  cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; bx[i] = box[i]; es[i] = 1; if (i + 1 < rank) st[i] = strides[i]; }
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<unsigned char*>(base), d, st, bx, es,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  YL_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (uint8)");
-  return 0;
-}
-
 // 4-D map over an NHWC fp32 activation: box = 32 channels x halo_w x halo_h x 1 image, dense [hy][hx][32] in shared memory;
 // coordinates outside the tensor (negative / past the edge / channels past C) read as zero.
 static int make_halo_tmap(CUtensorMap* tm, const float* in, int B, int H, int W, int C, int halo_w, int halo_h) {
