@@ -818,7 +818,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * w_slab_bytes) : "memory");
 #pragma unroll
           for (int ps = 0; ps < 2; ++ps) {
-            const float* src = p.wimg + ((size_t)ps * p.nslab + i_s) * p.Npad * 32;
+            const float* src = p.wimg + (((size_t)ps * p.nslab + i_s) * p.Npad + chunk_n0) * 32;
             const uint32_t dst = smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(dst), "l"(src), "r"(w_slab_bytes), "r"(bar) : "memory");
@@ -1247,13 +1247,20 @@ static void tc_pick_tile(int ks, int stride, int Hout, int Wout, TcPlan* pl) {
 // MODE 2 with weights too large to stay resident next to the halo ring: one K-slab (hi, lo) of W per A stage, from L2
 static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   (void)nslab;
-  const size_t fixed = (size_t)2 * (2 * TC_SLAB_BYTES + 2 * Npad * 128) + TC_AUX_BYTES + dw_bytes + 1024;
-  if (fixed + 2 * (size_t)pl->halo_bytes > (size_t)TC_SMEM_BUDGET) return false;
-  pl->Nc = Npad; pl->nchunks = 1; pl->wstream = 1; pl->stages = 2;
-  pl->halo_slots = 2;
-  while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
-  pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
-  return true;
+  // N chunks of equal size Nc <= 128 (one CTA row per chunk; each repeats the depthwise stage): fewest chunks that fit
+  for (int nch = 1; nch <= 8; ++nch) {
+    if ((Npad / 16) % nch) continue;
+    const int Nc = Npad / nch;
+    if (Nc > 128) continue;
+    const size_t fixed = (size_t)2 * (2 * TC_SLAB_BYTES + 2 * Nc * 128) + TC_AUX_BYTES + dw_bytes + 1024;
+    if (fixed + 2 * (size_t)pl->halo_bytes > (size_t)TC_SMEM_BUDGET) continue;
+    pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 1; pl->stages = 2;
+    pl->halo_slots = 2;
+    while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
+    pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
+    return true;
+  }
+  return false;
 }
 
 static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl, bool want_epi2 = false, int dw_stride = 1) {
@@ -1267,7 +1274,7 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
     if (pl->halo_pix == 0) return false;
   }
   const size_t dw_bytes = mode == 2 ? (size_t)(dw_ks * dw_ks + 1) * nslab * 32 * 4 : 0;
-  for (int nch = 1; nch <= 4; ++nch) {
+  for (int nch = 1; nch <= 8; ++nch) {
     int Nc = ((Npad / 16 + nch - 1) / nch) * 16;
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
     const size_t wbytes = (size_t)2 * nslab * Nc * 128;
@@ -1305,7 +1312,7 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
     pl->stages = stages; pl->smem = fixed + (size_t)stages * 2 * TC_SLAB_BYTES;
     return true;
   }
-  if (mode == 2 && Npad <= 128 && (N & 3) == 0) return tc_plan_stream(nslab, Npad, dw_bytes, pl);
+  if (mode == 2 && (N & 3) == 0) return tc_plan_stream(nslab, Npad, dw_bytes, pl);
   return false;
 }
 
