@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
             for (int ps = 0; ps < 2; ++ps)
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                           ::"r"(smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes), "l"(p.wimg + ((size_t)ps * p.nslab + s) * p.Npad * 32),
+                           ::"r"(smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes), "l"(p.wimg + (((size_t)ps * p.nslab + s) * p.Npad + chunk_n0) * 32),
                              "r"(w_slab_bytes), "r"(bar) : "memory");
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -1263,6 +1263,27 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   return false;
 }
 
+// MODE 0 with TMA-fed A tiles and a K too long for a resident weight image at one N chunk: every stage carries its own
+// K-slab of W (hi, lo) next to the A tile.  Returns false when it does not fit.
+static bool tc_plan_stream0(int N, int anchors, int max_chunks, TcPlan* pl) {
+  const int Npad = (N + 15) / 16 * 16;
+  for (int nch = 1; nch < max_chunks; ++nch) {        // only if it needs fewer N chunks than the resident plan
+    if ((Npad / 16) % nch) continue;
+    const int Nc = Npad / nch;
+    if (Nc > 128) continue;
+    const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
+    const size_t fixed = TC_AUX_BYTES + dense_bytes + 1024;
+    const size_t per_stage = (size_t)2 * TC_SLAB_BYTES + (size_t)2 * Nc * 128;
+    int stages = (int)((TC_SMEM_BUDGET - fixed) / per_stage);
+    if (stages < 2) continue;
+    if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+    pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 1; pl->stages = stages; pl->halo_slots = 0; pl->epi2 = 0;
+    pl->smem = fixed + stages * per_stage;
+    return true;
+  }
+  return false;
+}
+
 static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, TcPlan* pl, bool want_epi2 = false, int dw_stride = 1) {
   if (K < 8 || N < 8) return false;
   const int nslab = (K + 31) / 32;
@@ -1313,23 +1334,8 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
     return true;
   }
   if (mode == 2 && (N & 3) == 0) return tc_plan_stream(nslab, Npad, dw_bytes, pl);
+  if (mode == 0) return tc_plan_stream0(N, anchors, 9, pl);        // needs the TMA-fed A path (checked at launch)
   return false;
-}
-
-// MODE 0 with TMA-fed A tiles and a K too long for a resident weight image at one N chunk: every stage carries its own
-// K-slab of W (hi, lo) next to the A tile.  Returns false when it does not fit.
-static bool tc_plan_stream0(int N, int anchors, TcPlan* pl) {
-  const int Npad = (N + 15) / 16 * 16;
-  if (Npad > 128) return false;
-  const size_t dense_bytes = tc_dense_epi(N, anchors, Npad, 1) ? (size_t)4 * 32 * Npad * 4 : 0;
-  const size_t fixed = TC_AUX_BYTES + dense_bytes + 1024;
-  const size_t per_stage = (size_t)2 * TC_SLAB_BYTES + (size_t)2 * Npad * 128;
-  int stages = (int)((TC_SMEM_BUDGET - fixed) / per_stage);
-  if (stages < 2) return false;
-  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-  pl->Nc = Npad; pl->nchunks = 1; pl->wstream = 1; pl->stages = stages; pl->halo_slots = 0; pl->epi2 = 0;
-  pl->smem = fixed + stages * per_stage;
-  return true;
 }
 
 bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, int dw_stride) {
@@ -1415,8 +1421,9 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
              "shape does not fit the tcgen05 conv kernel");
   if (tma_a && pl.nchunks > 1) {             // N was chunked only because the weights do not fit: stream them instead
     TcPlan ps;
-    if (tc_plan_stream0(c.Cout, c.anchors, &ps)) pl = ps;
+    if (tc_plan_stream0(c.Cout, c.anchors, pl.nchunks, &ps)) pl = ps;
   }
+  YL_REQUIRE(!(mode == 0 && pl.wstream) || tma_a, "streamed weights need a 16-byte aligned input (TMA)");
   p.epi2 = pl.epi2;
   p.prod_warps = pl.epi2 ? 4 : TC_PROD_WARPS;
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
