@@ -81,7 +81,10 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
     const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
     // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
     // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
-    const bool big = (K >= 32 && op.cout >= 32) || use_tc == 2;
+    // rows of N % 4 != 0 floats are not 16-byte aligned: the tensor-core epilogues read residual / upsample sources with
+    // 16-byte loads, so that (unused by the reference models) combination stays on the SIMT kernel
+    const bool unaligned_addend = (op.cout & 3) != 0 && (res || up);
+    const bool big = ((K >= 32 && op.cout >= 32) || use_tc == 2) && !unaligned_addend;
     if (big && (op.cin & 3) == 0 && tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout, op.kind == YL_OP_DWPW && op.stride2 > 1 ? op.stride2 : 1))
     { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
   }
