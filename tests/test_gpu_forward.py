@@ -11,6 +11,25 @@ from oracle import model_ref
 pytestmark = pytest.mark.gpu
 
 
+def test_forward_u8_non_square_and_unsupported_shapes():
+    """Non-square inputs (even H, W % 16 == 0) take the uint8 entry too; shapes it cannot take are refused with ValueError
+    so that callers fall back to preprocess_batch + forward."""
+    import yololite_b200 as y
+    from conftest import synth_ckpt
+    ck = synth_ckpt("edge_n", 3, 64)
+    eng = y.YoloLiteB200(ck["state_dict"], ck["meta"], device="cuda:0")
+    mean = torch.tensor([0.485, 0.456, 0.406], device="cuda")
+    std = torch.tensor([0.229, 0.224, 0.225], device="cuda")
+    for (H, W) in ((96, 64), (34, 48), (64, 176)):
+        img = torch.randint(0, 256, (2, H, W, 3), dtype=torch.uint8, device="cuda", generator=torch.Generator(device="cuda").manual_seed(H + W))
+        x = ((img.flip(-1).float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()       # BGR -> RGB, normalise, CHW
+        for g, w in zip(eng.forward_u8(img), eng(x)):
+            assert float((g - w).abs().max()) <= 2e-4
+    assert not eng.supports_u8(33, 48) and not eng.supports_u8(64, 40)
+    with pytest.raises(ValueError):
+        eng.forward_u8(torch.zeros((1, 64, 40, 3), dtype=torch.uint8, device="cuda"))
+
+
 @pytest.mark.parametrize("model,nc,S", [("edge_n", 3, 64), ("edge_n", 80, 320), ("edge_n", 5, 96)])
 def test_forward_u8_matches_preprocess_plus_forward(model, nc, S):
     """yl_forward_u8 (normalisation folded into the fused stem kernel, one bf16 split for the integer pixels) against
