@@ -55,6 +55,7 @@ struct Stem2Params {
   float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
   int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
   int tiles_x, tiles_y, num_tiles;
+  int a1_stages;                       // stem operand stages: 2, or 1 when the 32-channel conv2 weights leave no room for two
   const unsigned char* __restrict__ in_u8;   // image mode: [B,H,W,3] uint8 BGR (the reference's cv2 image, tools/infer.py:436-453) read
                                        // directly: (u/255 - mean)/std is affine in the integer u, so it is folded into the stem
                                        // weights; u8 values are exact in ONE bf16 -> GEMM1 takes one instruction per k-step
@@ -128,6 +129,7 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t&
 }
 }  // namespace s2
 
+template <int A1S>      // stem operand stages (2; 1 when the 32-channel conv2 weights leave no room for two)
 __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params p, const __grid_constant__ CUtensorMap tmap) {
   using namespace s2;
   extern __shared__ unsigned char smem_unaligned[];
@@ -139,7 +141,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   unsigned char* w2s = smem;                                        // 1024-aligned (N2 % 16 == 0 -> 27 * N2 * 64 % 1024 == 0)
   unsigned char* wst = w2s + w2_bytes;                              // 6 KB
   unsigned char* a1 = wst + S2_WST_BYTES;                           // 2 stages x 3 splits x 8 KB (1024-aligned)
-  unsigned char* planes = a1 + 2 * S2_A1_STAGE;                     // 3 splits x 35904 B
+  unsigned char* planes = a1 + A1S * S2_A1_STAGE;           // 3 splits x 35904 B
   float* patch = reinterpret_cast<float*>(planes + 3 * S2_PLANE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + S2_PATCH_BYTES);
   uint64_t* a1_full = bars;            // [2]  producers (8 warps) -> MMA
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
       const int trem = tile % per_img;
       const int sy0 = 2 * S2_TH * (trem / p.tiles_x) - 1, sx0 = 2 * S2_TW * (trem % p.tiles_x) - 1;   // stem-output coords of halo (0,0)
       for (int j = 0; j < S2_MT; ++j, ++n) {
-        const uint32_t stage = n & 1u;
-        mbar_wait(smem_u32(&a1_empty[stage]), ((n >> 1) & 1u) ^ 1u);
+        const uint32_t stage = A1S == 2 ? (n & 1u) : 0u, aph = A1S == 2 ? ((n >> 1) & 1u) : (n & 1u);
+        mbar_wait(smem_u32(&a1_empty[stage]), aph ^ 1u);
         unsigned char* st = a1 + stage * S2_A1_STAGE;
         if (p.in_u8) {
 #pragma unroll
@@ -324,9 +326,9 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
       uint32_t n = 0, slot = 0, sphase = 0;
       auto gemm1 = [&](int j0, int j1) {
         for (int j = j0; j < j1; ++j, ++n) {
-          const uint32_t stage = n & 1u;
+          const uint32_t stage = A1S == 2 ? (n & 1u) : 0u, aph = A1S == 2 ? ((n >> 1) & 1u) : (n & 1u);
           mbar_wait(smem_u32(&acc1_free[slot]), sphase ^ 1u);
-          mbar_wait(smem_u32(&a1_full[stage]), (n >> 1) & 1u);
+          mbar_wait(smem_u32(&a1_full[stage]), aph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t d0 = tmem_base + S2_ACC1_COLS * slot;
           const uint64_t da0 = dA1 + (uint64_t)(stage * (S2_A1_STAGE >> 4));
@@ -543,16 +545,18 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static size_t stem2_smem_bytes(int N2) {
-  return (size_t)27 * N2 * 64 + S2_WST_BYTES + 2 * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 + (16 * 16 + 16) * 4 + 1024;
+static size_t stem2_smem_bytes(int N2, int a1_stages) {
+  return (size_t)27 * N2 * 64 + S2_WST_BYTES + (size_t)a1_stages * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 +
+         (16 * 16 + 16) * 4 + 1024;
 }
+static int stem2_a1_stages(int N2) { return stem2_smem_bytes(N2, 2) <= (size_t)227 * 1024 ? 2 : 1; }
 
 bool stem2_supported(const ConvParams& c) {
   const int N2 = (c.Cout + 15) / 16 * 16;
   // image mode: the folded-normalisation border terms cover the top / left padding only (even H, W: no bottom / right padding)
   const bool in_ok = c.in_u8 ? ((reinterpret_cast<uintptr_t>(c.in_u8) & 15) == 0 && (c.Hin & 1) == 0 && (c.Win & 15) == 0)
                              : ((reinterpret_cast<uintptr_t>(c.in) & 15) == 0 && (c.Win & 3) == 0);
-  return c.KS == 3 && c.stride == 2 && c.Cin == 32 && (c.Cout & 3) == 0 && N2 <= 32 && in_ok && stem2_smem_bytes(N2) <= (size_t)227 * 1024 && !c.res && !c.up &&
+  return c.KS == 3 && c.stride == 2 && c.Cin == 32 && (c.Cout & 3) == 0 && N2 <= 32 && in_ok && stem2_smem_bytes(N2, stem2_a1_stages(N2)) <= (size_t)227 * 1024 && !c.res && !c.up &&
          c.anchors <= 1 && c.bias != nullptr;
 }
 
@@ -571,10 +575,12 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
   const long long nt = (long long)p.B * p.tiles_x * p.tiles_y;
   YL_REQUIRE(nt < (1ll << 31) && (long long)p.B * p.Ho * p.Wo * p.Cout < (1ll << 40), "too many tiles");
   p.num_tiles = (int)nt;
-  const size_t smem = stem2_smem_bytes(p.N2);
+  p.a1_stages = stem2_a1_stages(p.N2);
+  const size_t smem = stem2_smem_bytes(p.N2, p.a1_stages);
   static thread_local bool attr_set = false;
   if (!attr_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   int gx = sm_count < p.num_tiles ? sm_count : p.num_tiles;
@@ -586,7 +592,8 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
     const unsigned int box[3] = {(unsigned)S2_PP, (unsigned)S2_PR, 3};
     if (int rc = make_tmap_f32(&tmap, p.in, 3, dims, strides, box, false)) return rc;
   }
-  stem2_kernel<<<gx, S2_THREADS, smem, st>>>(p, tmap);
+  if (p.a1_stages == 2) stem2_kernel<2><<<gx, S2_THREADS, smem, st>>>(p, tmap);
+  else stem2_kernel<1><<<gx, S2_THREADS, smem, st>>>(p, tmap);
   YL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
