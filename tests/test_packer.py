@@ -133,3 +133,20 @@ def test_stem_u8_matrix_reproduces_normalise_then_conv():
             a[30] = a[28] * a[29]
             got[:, sy, sx] = su @ a
     assert np.abs(got - want).max() < 1e-10
+
+
+def test_edge_n_program_shape():
+    """The fusions the kernels rely on: edge_n lowers to 40 ops -- one fused stem op (conv_stem + blocks.0.0 + blocks.0.1), every
+    depthwise conv of the UIR blocks riding in a YL_OP_DWPW (stride 2 included), no standalone depthwise op left."""
+    from yololite_b200 import _lib as L
+    ck, _ = case_ckpt("fwd_edge_n_320_nc80")
+    P = packer.lower(ck["state_dict"], ck["meta"])
+    kinds = [op["kind"] for op in P.ops]
+    assert len(P.ops) == 40 and kinds[0] == L.OP_STEM2 and P.ops[0]["b2_off"] >= 0 and P.ops[0]["w3_off"] >= 0
+    assert L.OP_DW not in kinds and L.OP_STEM not in kinds
+    dwpw = [op for op in P.ops if op["kind"] == L.OP_DWPW]
+    assert len(dwpw) == 21 and sum(op["stride2"] == 2 for op in dwpw) == 2 and {op["k2"] for op in dwpw} == {3, 5}
+    assert sum(op["res"] >= 0 for op in P.ops) == 10          # blocks 2.1-2.5 and 3.1-3.5 carry the skip connection
+    # unfused lowering keeps the reference's layer list: 45 backbone convs + 9 FPN + 12 head convs, head outputs merged per level
+    Pn = packer.lower(ck["state_dict"], ck["meta"], fuse_dwpw=False, fuse_stem=False)
+    assert len(Pn.ops) == 45 + 9 + 6 + 3
