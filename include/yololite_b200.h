@@ -9,7 +9,9 @@
  *     outputs are ordinary torch.Tensors) and passed as a raw DEVICE pointer unless the name says host;
  *   - the engine owns packed weights and scratch, nothing else;
  *   - all work is enqueued on the caller's stream (a cudaStream_t passed as void*), no host sync inside
- *     yl_forward / yl_postprocess / yl_preprocess -> graph-capturable;
+ *     yl_forward / yl_postprocess / yl_preprocess.  After yl_engine_plan for a shape, yl_forward / yl_engine_detect allocate
+ *     nothing and are graph-capturable (the first call for a NEW shape sizes the arena with cudaMalloc: plan before capturing);
+ *   - the caller's current CUDA device is never changed: entry points select the engine's (or the buffers') device and restore;
  *   - return value 0 = ok, negative = error; the message is in yl_last_error() (thread local);
  *   - there is NO CPU fallback: every call fails loudly without a CUDA device.
  */
@@ -23,7 +25,7 @@
 extern "C" {
 #endif
 
-#define YL_ABI_VERSION 3
+#define YL_ABI_VERSION 4
 
 typedef struct yl_engine yl_engine;
 
@@ -49,6 +51,8 @@ enum yl_op_kind {
 enum yl_act { YL_ACT_NONE = 0, YL_ACT_RELU = 1, YL_ACT_SILU = 2 };
 
 #define YL_SRC_INPUT (-1)          /* op.src: the network input x                                      */
+#define YL_SRC_FEATURE(i) (-(2 + (i))) /* op.src: externally supplied backbone feature i (NHWC fp32), yl_forward_features */
+#define YL_FEATURE_INDEX(src) (-(src) - 2)
 #define YL_DST_LEVEL(l) (-(1 + (l))) /* op.dst: write output level l ([B,A,S,S,5+C], model_v2.py:340-350) */
 
 typedef struct yl_op {
@@ -86,8 +90,10 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
                      int32_t n_buffers, int32_t n_levels, int32_t device, yl_engine** out);
 int yl_engine_destroy(yl_engine* e);
 
-/* Engine options.  key "tensor_cores": 1 (default) = run eligible convs on the tcgen05 3xTF32 kernel, 0 = fp32 SIMT
- * kernels only.  Unknown keys return an error.                                                          */
+/* Engine options.  "tensor_cores": 1 (default) = run eligible convs on the tcgen05 3xTF32 kernel, 0 = fp32 SIMT kernels only.
+ * "pdl": 1 (default) = launch the tcgen05 kernels with programmatic dependent launch (prologue overlaps the previous kernel's
+ * tail).  "graph": 1 = capture each distinct call (same pointers, shape and thresholds) once into a CUDA graph and replay it
+ * (default 0; the first call with new pointers runs eagerly, the second captures).  Unknown keys return an error.          */
 int yl_engine_set_option(yl_engine* e, const char* key, int32_t value);
 
 /* Shapes of the output levels for an input of B x 3 x H x W: shapes[l*4 + {0,1,2,3}] = A, S_h, S_w, 5+C.
@@ -108,6 +114,23 @@ int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, fl
  * (YL_OP_STEM2 with w3_off), even H and W % 16 == 0; returns -1 otherwise (callers fall back to yl_preprocess_batch + yl_forward). */
 int yl_forward_u8(yl_engine* e, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, float* const* level_out,
                   void* stream);
+
+/* FPN + heads only (scripts/model/model_v2.py:124-133,201-224 / :289-294,359-377): the layer program reads the backbone's feature
+ * maps instead of an image (ops with src = YL_SRC_FEATURE(i); built by the packer's `lower(..., from_features=True)`).
+ * feats[i]: NHWC fp32 [B,H_i,W_i,C_i] on the device (a torch channels_last tensor is exactly this), finest level first
+ * ([c2,] c3, c4, c5 -- what timm's features_only backbone returns at model_v2.py:195,353); feat_dims[i*3 + {0,1,2}] = H_i, W_i, C_i. */
+int yl_engine_plan_features(yl_engine* e, int32_t B, const int32_t* feat_dims, int32_t n_feats, int32_t* shapes /* n_levels*4 */);
+int yl_forward_features(yl_engine* e, const float* const* feats, const int32_t* feat_dims, int32_t n_feats, int32_t B,
+                        float* const* level_out, void* stream);
+
+/* model(x) + postprocess in ONE call (tools/infer.py:456-493 for a batch): exactly one of x (fp32 NCHW, normalised) and
+ * images_bgr (uint8 HWC BGR, see yl_forward_u8) is non-null.  The logits stay in engine-owned level buffers (yl_engine_levels);
+ * outputs as yl_postprocess_ex.  With the "graph" option the whole call is one CUDA graph launch.                          */
+int yl_engine_detect(yl_engine* e, const float* x, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, int32_t img_size,
+                     float conf, double iou, int32_t max_det_per_class, int32_t cap, float* boxes, float* scores, int64_t* classes,
+                     int64_t* anchor_idx, int32_t* counts, float* packed, void* stream);
+/* Device pointers / shapes (n_levels*4: A, S_h, S_w, 5+C) of the engine-owned level buffers of the current plan.           */
+int yl_engine_levels(yl_engine* e, float** level_ptrs /* n_levels */, int32_t* shapes /* n_levels*4, may be NULL */);
 
 /* Same as yl_forward but brackets every op with CUDA events on `stream` and returns the device time of each
  * op in milliseconds (op_ms[n_ops]); synchronises the stream.  Used by bench.py for the per-kernel roofline. */
@@ -146,6 +169,16 @@ int yl_postprocess(const float* const* level_logits, const int32_t* level_dims, 
                    float* boxes, float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts,
                    void* scratch, size_t scratch_bytes, void* stream);
 
+/* Same with optional outputs: any of boxes / scores / classes / anchor_idx / counts may be NULL when `packed` is given.
+ * packed: [B][cap + 1][6] fp32, row 0 of an image = (count = min(K, cap), overflow flag, K, 0, 0, 0), rows 1..count =
+ * (x1, y1, x2, y2, score, class) -- the fixed-capacity payload of the multi-GPU gather written by the
+ * kernel itself, so that the gather is ONE collective with no packing pass.                                                */
+int yl_postprocess_ex(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels,
+                      int32_t B, int32_t D, int32_t img_size, float conf, double iou,
+                      int32_t max_det_per_class, int32_t cap,
+                      float* boxes, float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts, float* packed,
+                      void* scratch, size_t scratch_bytes, void* stream);
+
 /* Decode only (utils_ms.py:25-123): box [B,N,4], obj [B,N,1], cls [B,N,C] -- obj/cls are raw logits.   */
 int yl_decode(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels, int32_t B,
               int32_t D, int32_t img_size, float* box, float* obj, float* cls, void* stream);
@@ -162,7 +195,7 @@ int yl_preprocess_batch(const uint8_t* src, int32_t B, int32_t h0, int32_t w0, f
                         int32_t left, int32_t top, void* stream);
 
 /* Process-wide launch counters: key "tc_launches" (tcgen05 conv kernel), "simt_launches" (fp32 SIMT conv kernels),
- * "post_launches".  Unknown key -> -1.  Lets tests assert WHICH kernel a call used.                       */
+ * "post_launches", "graph_launches" / "graph_captures" (CUDA graph replays / captures), "prepares" (launch records built).  Unknown key -> -1.  Lets tests assert WHICH kernel a call used.                       */
 long long yl_stat(const char* key);
 
 const char* yl_last_error(void);

@@ -160,6 +160,14 @@ def make_meta(model: str = "edge_n", num_classes: int = 80, img_size: int = 640,
         # arch with tf_efficientnet_* backbones which have no in-repo structural pin.
         "ms_n_mnv4": dict(arch="YOLOLiteMS", backbone="mobilenetv4_conv_small", depth_multiple=1.0,
                           width_multiple=1.0, fpn_channels=196, head_depth=1),
+        "ms_m_mnv4": dict(arch="YOLOLiteMS", backbone="mobilenetv4_conv_small", depth_multiple=1.0,
+                          width_multiple=1.0, fpn_channels=328, head_depth=2),
+        # configs/models/yololite_n.yaml / yololite_m.yaml: the oracle restates their FPN + heads only (forward_ref(feats=...));
+        # the tf_efficientnet_lite* backbones are un-vendored timm code with no in-repo structural pin
+        "yololite_n": dict(arch="YOLOLiteMS", backbone="tf_efficientnet_lite0", depth_multiple=1.0, width_multiple=1.0,
+                           fpn_channels=196, head_depth=1),
+        "yololite_m": dict(arch="YOLOLiteMS", backbone="tf_efficientnet_lite2", depth_multiple=1.0, width_multiple=1.0,
+                           fpn_channels=328, head_depth=2),
     }
     m = dict(yamls[model])
     m["num_classes"] = num_classes
@@ -173,7 +181,12 @@ def make_meta(model: str = "edge_n", num_classes: int = 80, img_size: int = 640,
     }
 
 
-def state_spec(meta: dict) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
+# channels of the [c2, c3, c4, c5] taps of timm's tf_efficientnet_lite0 / lite2 `features_only` (reductions 4, 8, 16, 32), from
+# timm's published arch definitions; used only to give the FPN + head restatement realistic input widths (unpinned)
+FEATURE_CHANNELS = {"tf_efficientnet_lite0": (24, 40, 112, 320), "tf_efficientnet_lite2": (24, 48, 120, 352)}
+
+
+def state_spec(meta: dict, feat_chs: Optional[Sequence[int]] = None) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
     """Every state_dict entry the reference module tree holds for this meta: key -> (shape, kind).
 
     kind in {"conv", "dw", "head_w", "bias", "obj_b", "cls_b", "box_b", "bn_w", "bn_b", "bn_rm", "bn_rv",
@@ -189,18 +202,20 @@ def state_spec(meta: dict) -> "OrderedDict[str, Tuple[Tuple[int, ...], str]]":
         spec[prefix + ".running_var"] = ((c,), "bn_rv")
         spec[prefix + ".num_batches_tracked"] = ((), "bn_nbt")
 
-    blocks, feats = backbone_layers(cfg["backbone"])
-    stem = feats[0]["num_chs"]
-    spec["backbone.conv_stem.weight"] = ((stem, 3, 3, 3), "conv")
-    bn("backbone.bn1", stem)
-    for b in blocks:
-        for c in b["convs"]:
-            spec[f"backbone.{c['key']}.weight"] = ((c["cout"], c["cin"] // c["groups"], c["k"], c["k"]),
-                                                    "dw" if c["groups"] > 1 else "conv")
-            bn(f"backbone.{c['bn']}", c["cout"])
-
     take = 4 if cfg["use_p2"] else 3
-    chs = [f["num_chs"] for f in feats[-take:]]
+    if feat_chs is not None:          # FPN + heads only: the backbone (and its parameters) live elsewhere
+        chs = list(feat_chs)[-take:]
+    else:
+        blocks, feats = backbone_layers(cfg["backbone"])
+        stem = feats[0]["num_chs"]
+        spec["backbone.conv_stem.weight"] = ((stem, 3, 3, 3), "conv")
+        bn("backbone.bn1", stem)
+        for b in blocks:
+            for c in b["convs"]:
+                spec[f"backbone.{c['key']}.weight"] = ((c["cout"], c["cin"] // c["groups"], c["k"], c["k"]),
+                                                        "dw" if c["groups"] > 1 else "conv")
+                bn(f"backbone.{c['bn']}", c["cout"])
+        chs = [f["num_chs"] for f in feats[-take:]]
     Fc, d, C = cfg["fpn_channels"], cfg["depth"], cfg["num_classes"]
     cpu = cfg["arch"] == "yololitems_cpu"
 
@@ -306,14 +321,15 @@ def _head(ctx, p, name, A, C, depth):    # model_v2.py:42-53, :340-350
     return t.permute(0, 1, 3, 4, 2).contiguous()
 
 
-def forward_ref(sd: Dict[str, torch.Tensor], meta: dict, x: torch.Tensor, calibrate: bool = False,
-                return_feats: bool = False):
-    """Reference forward: x [B,3,H,W] fp32 NCHW -> list of [B,A,S,S,5+C] per level (model_v2.py:352-377)."""
+def forward_ref(sd: Dict[str, torch.Tensor], meta: dict, x: Optional[torch.Tensor], calibrate: bool = False,
+                return_feats: bool = False, feats: Optional[Sequence[torch.Tensor]] = None):
+    """Reference forward: x [B,3,H,W] fp32 NCHW -> list of [B,A,S,S,5+C] per level (model_v2.py:352-377).  With `feats`
+    ([c2,] c3, c4, c5 NCHW, what `self.backbone(x)` returns at model_v2.py:195,353) the backbone is skipped: FPN + heads only."""
     cfg = model_cfg_from_meta(meta)
     ctx = _Ctx(sd, calibrate)
     with torch.no_grad():
-        feats = backbone_forward(ctx, x, cfg["backbone"])
         take = 4 if cfg["use_p2"] else 3
+        feats = list(feats) if feats is not None else backbone_forward(ctx, x, cfg["backbone"])
         feats = feats[-take:]
         cpu = cfg["arch"] == "yololitems_cpu"
         smooth = _dw_block if cpu else _dense_block
@@ -355,7 +371,19 @@ def _gen(key: str, seed: int) -> torch.Generator:
     return g
 
 
-def synth_checkpoint(meta: dict, seed: int = 0, obj_bias_shift: float = 0.0, calib_size: int = 160) -> dict:
+def synth_features(B: int, size: int, chs: Sequence[int], seed: int = 0, reductions: Sequence[int] = (4, 8, 16, 32)):
+    """Synthetic backbone taps for an image of `size` px: [B,C_i,size/r_i,size/r_i] NCHW, half-normal (post-activation-like)."""
+    reds = list(reductions)[-len(chs):]
+    out = []
+    for i, (c, r) in enumerate(zip(chs, reds)):
+        g = torch.Generator().manual_seed(7000 + 31 * seed + i)
+        s = -(-size // r)
+        out.append(torch.randn(B, c, s, s, generator=g).abs_().mul_(0.8))
+    return out
+
+
+def synth_checkpoint(meta: dict, seed: int = 0, obj_bias_shift: float = 0.0, calib_size: int = 160,
+                     feat_chs: Optional[Sequence[int]] = None) -> dict:
     """{"state_dict", "meta"} with per-key seeded weights and data-calibrated BN statistics.
 
     Every tensor is drawn from its own generator seeded by crc32(key)^seed, so the result does not depend
@@ -364,7 +392,7 @@ def synth_checkpoint(meta: dict, seed: int = 0, obj_bias_shift: float = 0.0, cal
     """
     sd: Dict[str, torch.Tensor] = OrderedDict()
     C = model_cfg_from_meta(meta)["num_classes"]
-    for key, (shape, kind) in state_spec(meta).items():
+    for key, (shape, kind) in state_spec(meta, feat_chs).items():
         g = _gen(key, seed)
         if kind in ("conv", "dw"):
             fan_in = shape[1] * shape[2] * shape[3]
@@ -392,9 +420,12 @@ def synth_checkpoint(meta: dict, seed: int = 0, obj_bias_shift: float = 0.0, cal
         else:
             raise AssertionError(kind)
         sd[key] = t.float() if kind != "bn_nbt" else t
-    xc = torch.randn(4, 3, calib_size, calib_size, generator=_gen("calib", seed))
     m = dict(meta)
-    forward_ref(sd, m, xc, calibrate=True)
+    if feat_chs is not None:
+        forward_ref(sd, m, None, calibrate=True, feats=synth_features(2, calib_size, feat_chs, seed=seed + 100))
+    else:
+        xc = torch.randn(4, 3, calib_size, calib_size, generator=_gen("calib", seed))
+        forward_ref(sd, m, xc, calibrate=True)
     # p6 branch statistics when the branch is not part of the graph: leave (0,1).
     return {"state_dict": sd, "meta": meta}
 

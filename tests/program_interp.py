@@ -19,7 +19,8 @@ def run_program(P, x):
     levels = {}
     for op in P.ops:
         cin, cout, k, s = op["cin"], op["cout"], op["k"], op["stride"]
-        src = x if op["src"] < 0 else bufs[op["src"]]          # NCHW tensors inside the interpreter
+        # NCHW tensors inside the interpreter; x is the image, or the list of backbone features for a from_features program
+        src = x[-op["src"] - 2] if op["src"] <= -2 else x if op["src"] < 0 else bufs[op["src"]]
         assert src.shape[1] == cin, (op, src.shape)
         bias = None if op["b_off"] < 0 else blob[op["b_off"]:op["b_off"] + cout]
         if op["kind"] == 4:       # fused stem (3x3 s2, 32 ch, ReLU) -> 3x3 s2 conv

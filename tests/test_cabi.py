@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(lib, name), name
     assert sorted(y.EXPORTS) == decl
-    assert lib.yl_abi_version() == 3
+    assert lib.yl_abi_version() == 4
 
 
 def test_op_struct_layout_matches_header():

@@ -166,3 +166,29 @@ def test_full_batch_properties_at_bench_size():
         assert b.min() >= 0 and b.max() <= 639
     want = post_ref.detect_ref([l[:2].cpu().numpy() for l in lv], 640, 0.25, 0.5, 300)
     _check(r1[:2], want, "bench-size")
+
+
+@pytest.mark.parametrize("name", ["post_c3", "post_c1", "post_c7_a2"])
+def test_coco_dets_wrapper_matches_reference_golden(name):
+    """The PRODUCT's evaluation wrapper post.decode_batch_to_coco_dets (conf 0.001, iou 0.65, no cap, (cx,cy,w,h) boxes,
+    category_id = class + 1) against the dets the unmodified scripts/helpers/helpers.py:86-153 produced for the same
+    logits (tests/golden/post_coco.json, written by oracle/make_golden.py)."""
+    import json
+    import os
+    import yololite_b200 as y
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "post_coco.json")) as f:
+        want = json.load(f)[name]
+    g = golden(name + ".npz")
+    lv = [torch.from_numpy(np.ascontiguousarray(l)).cuda() for l in _glevels(g)]
+    got = y.decode_batch_to_coco_dets(lv, int(g["img"]))
+    assert [len(x) for x in got] == [len(x) for x in want]
+    for b, (gi, wi) in enumerate(zip(got, want)):
+        assert [d["category_id"] for d in gi] == [d["category_id"] for d in wi], (name, b)
+        assert all(set(d) == {"category_id", "bbox", "score"} and isinstance(d["category_id"], int) for d in gi)
+        np.testing.assert_allclose([d["score"] for d in gi], [d["score"] for d in wi], rtol=0, atol=1e-5)
+        np.testing.assert_allclose(np.array([d["bbox"] for d in gi]).reshape(-1, 4), np.array([d["bbox"] for d in wi]).reshape(-1, 4),
+                                   rtol=0, atol=1e-3)
+    # add_one=False keeps the raw class index (helpers.py:86 signature)
+    raw = y.decode_batch_to_coco_dets(lv, int(g["img"]), add_one=False)
+    assert [d["category_id"] + 1 for d in raw[0]] == [d["category_id"] for d in want[0]]

@@ -26,6 +26,12 @@ class YlOp(ctypes.Structure):
 OP_STEM, OP_CONV, OP_DW, OP_DWPW, OP_STEM2 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
 SRC_INPUT = -1
+ABI_VERSION = 4
+
+
+def src_feature(i: int) -> int:
+    """op.src of externally supplied backbone feature i (YL_SRC_FEATURE in the header)."""
+    return -(2 + i)
 
 _lib = None
 
@@ -47,6 +53,16 @@ _SIGNATURES = {
     "yl_postprocess": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
                                       ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_double, ctypes.c_int32,
                                       ctypes.c_int32, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "yl_postprocess_ex": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
+                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_double, ctypes.c_int32,
+                                         ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    "yl_engine_plan_features": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_int32), ctypes.c_int32,
+                                               ctypes.POINTER(ctypes.c_int32)]),
+    "yl_forward_features": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
+                                           ctypes.POINTER(_P), _P]),
+    "yl_engine_detect": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_float,
+                                        ctypes.c_double, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "yl_engine_levels": (ctypes.c_int, [_P, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32)]),
     "yl_decode": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32), ctypes.c_int32, ctypes.c_int32,
                                  ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "yl_preprocess": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32,

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 #include "../../include/yololite_b200.h"
@@ -11,7 +12,7 @@
 namespace yl {
 
 void set_error(const std::string& msg);
-extern long long g_tc_launches, g_simt_launches, g_post_launches;
+extern std::atomic<long long> g_tc_launches, g_simt_launches, g_post_launches;
 
 #define YL_CHECK_CUDA(expr)                                                                   \
   do {                                                                                        \

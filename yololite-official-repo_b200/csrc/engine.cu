@@ -1,21 +1,77 @@
 // C ABI + layer-program executor (see include/yololite_b200.h).
+//
+// yl_engine_plan sizes everything once per input shape (activation arena, output-level buffers, postprocess scratch); per op the
+// launch record of the tcgen05 kernels (kernel parameters + tensor maps, launch.cuh) is cached against the pointers it was
+// built for, so a steady-state yl_forward is a list of kernel launches: no planning, no cuTensorMapEncodeTiled, no allocation.
+// Kernels are launched with programmatic dependent launch (their prologue overlaps the previous kernel's tail) and, with the
+// "graph" option, the whole call (forward, or forward + postprocess for yl_engine_detect) is captured once into a CUDA graph
+// and replayed.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
 
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace yl {
 
 static thread_local std::string g_err;
-long long g_tc_launches = 0, g_simt_launches = 0, g_post_launches = 0;
+std::atomic<long long> g_tc_launches{0}, g_simt_launches{0}, g_post_launches{0}, g_graph_launches{0}, g_graph_captures{0},
+    g_prepares{0};
 void set_error(const std::string& msg) { g_err = msg; }
 
 struct BufShape {
   int H = 0, W = 0, C = 0;
   size_t off = 0, bytes = 0;
+};
+
+// the caller's current device is restored on return: the engine never changes it behind torch's back
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  int enter(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return -2; }
+    if (prev != dev) {
+      if (cudaSetDevice(dev) != cudaSuccess) { cudaGetLastError(); return -2; }
+      changed = true;
+    }
+    return 0;
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+constexpr int MAX_FEATS = 8, MAX_LEVELS = 8;
+
+// launch record of one op, valid for exactly these pointers
+struct OpRec {
+  const void *in = nullptr, *in_u8 = nullptr, *out = nullptr, *res = nullptr, *up = nullptr;
+  int kind = 0;                 // 1 tcgen05 conv, 2 fused stem
+  TcLaunch tc;
+  Stem2Launch s2;
+};
+struct OpCache {
+  std::vector<OpRec> recs;
+  size_t next = 0;
+};
+
+// identity of one yl_forward / yl_engine_detect call: the captured graph bakes all of it in
+struct CallKey {
+  const void* x = nullptr; const void* x_u8 = nullptr;
+  const void* feats[MAX_FEATS] = {};
+  const void* levels[MAX_LEVELS] = {};
+  const void* det[6] = {};       // boxes, scores, classes, anchor_idx, counts, packed
+  int B = 0, H = 0, W = 0, detect = 0, img_size = 0, max_det = 0, cap = 0, use_tc = 0, pdl = 0;
+  float conf = 0.f;
+  double iou = 0.0;
+};
+struct GraphRec {
+  CallKey key;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  unsigned long long last_use = 0;
 };
 
 }  // namespace yl
@@ -25,16 +81,26 @@ struct yl_engine {
   std::vector<yl_op> ops;
   float* d_blob = nullptr;
   size_t blob_floats = 0;
-  int n_buffers = 0, n_levels = 0;
+  int n_buffers = 0, n_levels = 0, n_feats = 0;
   // plan
   int B = 0, H = 0, W = 0;
+  std::vector<int> feat_dims;    // n_feats * 3 (H, W, C) of the planned shape
   std::vector<yl::BufShape> bufs;
   std::vector<int> level_shape;  // n_levels * 4
+  std::vector<size_t> level_off; // engine-owned level buffers (yl_engine_detect) inside the arena
   std::vector<int> op_hout, op_wout, op_hin, op_win, op_hu, op_wu;
+  size_t stem_tmp_off = 0;       // unfused stem fallback: intermediate [B,Ho,Wo,C] buffer (only when the fused kernel cannot run)
+  bool has_stem_tmp = false;
+  size_t post_scratch_off = 0, post_scratch_bytes = 0;
+  long long n_anchors = 0;
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
-  int use_tc = 1;
+  int use_tc = 1, pdl = 1, use_graph = 0;
   int sm_count = 148;
+  std::vector<yl::OpCache> cache;
+  std::vector<yl::GraphRec> graphs;
+  unsigned long long tick = 0;
+  cudaStream_t cap_stream = nullptr;
 };
 
 namespace yl {
@@ -42,12 +108,13 @@ namespace yl {
 int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st);
 bool tc_supported(int K, int N, int anchors, int mode, int dw_ks, int Hout, int Wout, int dw_stride);
 bool stem2_supported(const ConvParams& c);
-int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st);
+int post_run(const float* const* level_logits, const int32_t* level_dims, int n_levels, int B, int D, int img_size, float conf, double iou,
+             int max_det_per_class, int cap, float* boxes, float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts,
+             float* packed, void* scratch, size_t scratch_bytes, cudaStream_t st);
 
-static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
-                  int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st,
-                  const unsigned char* in_u8 = nullptr) {
-  ConvParams p{};
+static void fill_params(ConvParams& p, const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out,
+                        int B, int hin, int win, int hout, int wout, int hu, int wu, const unsigned char* in_u8) {
+  p = ConvParams{};
   p.in = in;
   p.in_u8 = in_u8;
   p.w = blob + op.w_off;
@@ -69,25 +136,27 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
     p.Cin = op.k2;                                // K of the second conv = 9 * stem channels
     p.b2 = op.b2_off >= 0 ? blob + op.b2_off : nullptr;     // fused pointwise conv after conv2 ([cout][cout] + cout biases)
     p.act2 = op.act2;
-    ++g_tc_launches;
-    static const int old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
-    if (op.w3_off >= 0 && !old_stem && stem2_supported(p)) return launch_stem2(p, blob + op.w3_off, sm_count, st);
-    YL_REQUIRE(!in_u8, "uint8 image input needs the fused bf16 stem kernel (16/32-channel second conv, even H, W % 16 == 0)");
-    YL_REQUIRE(!p.b2, "YL_OP_STEM2 with a fused pointwise conv needs the bf16-triple kernel (w3_off, 16 channels, W % 4 == 0)");
-    return launch_tc_conv(p, blob + op.wt_off, 3, sm_count, st);
   }
-  if (use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW)) {
-    const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
-    const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
-    // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at
-    // ~2 TB/s on the SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2)
-    // rows of N % 4 != 0 floats are not 16-byte aligned: the tensor-core epilogues read residual / upsample sources with
-    // 16-byte loads, so that (unused by the reference models) combination stays on the SIMT kernel
-    const bool unaligned_addend = (op.cout & 3) != 0 && (res || up);
-    const bool big = ((K >= 32 && op.cout >= 32) || use_tc == 2) && !unaligned_addend;
-    if (big && (op.cin & 3) == 0 && tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout, op.kind == YL_OP_DWPW && op.stride2 > 1 ? op.stride2 : 1))
-    { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
-  }
+}
+
+// which tcgen05 mode (0 pointwise, 1 dense KxK, 2 depthwise -> pointwise) runs this op, or -1 for the fp32 SIMT kernels
+static int tc_mode_for(const yl_op& op, const ConvParams& p, int use_tc, int hout, int wout) {
+  if (!(use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW))) return -1;
+  const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
+  const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
+  // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at ~2 TB/s on the
+  // SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2).  Rows of N % 4 != 0 floats are not
+  // 16-byte aligned: the tensor-core epilogues read residual / upsample sources with 16-byte loads, so that (unused by the
+  // reference models) combination stays on the SIMT kernel, as does a fused depthwise stage with N % 4 != 0.
+  const bool unaligned = (op.cout & 3) != 0 && (p.res || p.up || mode == 2);
+  const bool big = ((K >= 32 && op.cout >= 32) || use_tc == 2) && !unaligned;
+  if (big && (op.cin & 3) == 0 &&
+      tc_supported(K, op.cout, op.anchors, mode, op.kind == YL_OP_DWPW ? op.k2 : 0, hout, wout, op.kind == YL_OP_DWPW && op.stride2 > 1 ? op.stride2 : 1))
+    return mode;
+  return -1;
+}
+
+static int launch_simt(const yl_op& op, const ConvParams& p, cudaStream_t st) {
   ++g_simt_launches;
   switch (op.kind) {
     case YL_OP_STEM: return launch_stem(p, st);
@@ -99,24 +168,85 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
   return 0;
 }
 
-static int plan(yl_engine* e, int B, int H, int W) {
-  if (e->B == B && e->H == H && e->W == W && e->arena) return 0;
-  YL_REQUIRE(B >= 1 && H >= 1 && W >= 1, "B,H,W must be positive");
+static const int g_old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
+
+// YL_OP_STEM2 when the fused bf16 kernel cannot take the shape (W % 4 != 0, more than 32 conv2 channels ...): the older tf32
+// kernel for conv_stem -> conv2, then the fused pointwise conv (timm blocks.0.1) as a separate SIMT launch through `tmp`.
+static int run_stem2_unfused(const yl_op& op, const ConvParams& p, const float* blob, float* tmp, int sm_count, cudaStream_t st) {
+  YL_REQUIRE(!p.in_u8, "uint8 image input needs the fused bf16 stem kernel (16/32-channel second conv, even H, W % 16 == 0)");
+  ConvParams q = p;
+  if (p.b2) {
+    YL_REQUIRE(tmp != nullptr, "unfused stem fallback needs the intermediate buffer (plan the engine for this shape first)");
+    q.out = tmp; q.b2 = nullptr; q.act2 = YL_ACT_NONE;
+  }
+  ++g_tc_launches;
+  if (int rc = launch_tc_conv(q, blob + op.wt_off, 3, sm_count, st)) return rc;
+  if (p.b2) {
+    ConvParams r{};
+    r.in = tmp; r.w = p.b2; r.bias = p.b2 + (size_t)op.cout * op.cout; r.out = p.out;
+    r.B = p.B; r.Hin = p.Hout; r.Win = p.Wout; r.Cin = op.cout; r.Hout = p.Hout; r.Wout = p.Wout; r.Cout = op.cout;
+    r.KS = 1; r.stride = 1; r.pad = 0; r.act = p.act2;
+    ++g_simt_launches;
+    return launch_conv_gemm(r, st);
+  }
+  return 0;
+}
+
+// One op, no caching (yl_run_op and the profile path).
+static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
+                  int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st,
+                  const unsigned char* in_u8 = nullptr, float* stem_tmp = nullptr) {
+  ConvParams p;
+  fill_params(p, op, blob, in, res, up, out, B, hin, win, hout, wout, hu, wu, in_u8);
+  if (op.kind == YL_OP_STEM2) {
+    if (op.w3_off >= 0 && !g_old_stem && stem2_supported(p)) {
+      ++g_tc_launches;
+      Stem2Launch L;
+      if (int rc = stem2_prepare(p, blob + op.w3_off, sm_count, &L)) return rc;
+      return stem2_launch(L, st, 0);
+    }
+    return run_stem2_unfused(op, p, blob, stem_tmp, sm_count, st);
+  }
+  const int mode = tc_mode_for(op, p, use_tc, hout, wout);
+  if (mode >= 0) { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
+  return launch_simt(op, p, st);
+}
+
+static void drop_graphs(yl_engine* e) {
+  for (auto& g : e->graphs) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (g.graph) cudaGraphDestroy(g.graph);
+  }
+  e->graphs.clear();
+}
+
+static int plan(yl_engine* e, int B, int H, int W, const int32_t* feat_dims) {
+  const bool same_feats = e->n_feats == 0 || (feat_dims && std::equal(e->feat_dims.begin(), e->feat_dims.end(), feat_dims));
+  if (e->B == B && e->H == H && e->W == W && e->arena && same_feats) return 0;
+  YL_REQUIRE(B >= 1, "B must be positive");
+  YL_REQUIRE(e->n_feats > 0 || (H >= 1 && W >= 1), "H,W must be positive");
+  YL_REQUIRE(e->n_feats == 0 || feat_dims, "this layer program reads backbone features: pass their dimensions");
   const int nops = (int)e->ops.size();
   std::vector<BufShape> bufs(e->n_buffers);
   std::vector<int> lvl(e->n_levels * 4, 0);
   e->op_hout.assign(nops, 0); e->op_wout.assign(nops, 0); e->op_hin.assign(nops, 0); e->op_win.assign(nops, 0);
   e->op_hu.assign(nops, 0); e->op_wu.assign(nops, 0);
+  size_t stem_tmp_bytes = 0;
   for (int i = 0; i < nops; ++i) {
     const yl_op& op = e->ops[i];
     int hin, win, cin;
     if (op.src == YL_SRC_INPUT) { hin = H; win = W; cin = 3; }
-    else {
+    else if (op.src <= YL_SRC_FEATURE(0)) {
+      const int f = YL_FEATURE_INDEX(op.src);
+      YL_REQUIRE(f < e->n_feats, "feature input index out of range");
+      hin = feat_dims[f * 3]; win = feat_dims[f * 3 + 1]; cin = feat_dims[f * 3 + 2];
+      YL_REQUIRE(hin >= 1 && win >= 1, "feature dimensions must be positive");
+    } else {
       YL_REQUIRE(op.src >= 0 && op.src < e->n_buffers, "op.src out of range");
       hin = bufs[op.src].H; win = bufs[op.src].W; cin = bufs[op.src].C;
       YL_REQUIRE(hin > 0, "op reads a buffer that was never written");
     }
-    YL_REQUIRE(cin == op.cin, "op.cin does not match the source buffer");
+    YL_REQUIRE(cin == op.cin, "op.cin does not match the source tensor");
     const int pad = op.k / 2;
     if (op.kind == YL_OP_STEM2) {                 // two stacked 3x3 s2 convs: size after the stem first
       hin = (hin + 2 - 3) / 2 + 1; win = (win + 2 - 3) / 2 + 1;
@@ -130,7 +260,13 @@ static int plan(yl_engine* e, int B, int H, int W) {
       wout = (win + 2 * (op.k2 / 2) - op.k2) / s2 + 1;
     }
     YL_REQUIRE(hout >= 1 && wout >= 1, "input too small for the network");
-    if (op.kind == YL_OP_STEM2) { hin = H; win = W; }
+    if (op.kind == YL_OP_STEM2) {
+      hin = H; win = W;
+      // the fused kernel needs W % 4 == 0 (TMA row pitch) and <= 32 conv2 channels; otherwise the unfused fallback runs and a
+      // fused pointwise conv needs an intermediate tensor
+      const bool fused_ok = op.w3_off >= 0 && !g_old_stem && (W & 3) == 0 && op.cout <= 32 && (op.cout & 3) == 0;
+      if (!fused_ok && op.b2_off >= 0) stem_tmp_bytes = std::max(stem_tmp_bytes, (size_t)B * hout * wout * op.cout * sizeof(float));
+    }
     e->op_hin[i] = hin; e->op_win[i] = win; e->op_hout[i] = hout; e->op_wout[i] = wout;
     if (op.dst >= 0) {
       YL_REQUIRE(op.dst < e->n_buffers, "op.dst out of range");
@@ -152,14 +288,163 @@ static int plan(yl_engine* e, int B, int H, int W) {
     }
   }
   size_t off = 0;
-  for (auto& b : bufs) { b.off = off; off += (b.bytes + 255) / 256 * 256; }
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+  for (auto& b : bufs) b.off = take(b.bytes);
+  e->stem_tmp_off = take(stem_tmp_bytes);
+  e->has_stem_tmp = stem_tmp_bytes > 0;
+  // engine-owned output levels + postprocess scratch (yl_engine_detect)
+  std::vector<size_t> loff(e->n_levels);
+  long long N = 0;
+  for (int l = 0; l < e->n_levels; ++l) {
+    const long long n = (long long)lvl[l * 4] * lvl[l * 4 + 1] * lvl[l * 4 + 2];
+    N += n;
+    loff[l] = take((size_t)B * n * lvl[l * 4 + 3] * sizeof(float));
+  }
+  const size_t sbytes = yl_postprocess_scratch_bytes(B, N);
+  const size_t soff = take(sbytes);
   if (off > e->arena_bytes) {
     if (e->arena) YL_CHECK_CUDA(cudaFree(e->arena));
     e->arena = nullptr; e->arena_bytes = 0;
     YL_CHECK_CUDA(cudaMalloc(&e->arena, off));
     e->arena_bytes = off;
   }
-  e->bufs = bufs; e->level_shape = lvl; e->B = B; e->H = H; e->W = W;
+  e->bufs = bufs; e->level_shape = lvl; e->level_off = loff; e->n_anchors = N;
+  e->post_scratch_off = soff; e->post_scratch_bytes = sbytes;
+  e->B = B; e->H = H; e->W = W;
+  if (e->n_feats) e->feat_dims.assign(feat_dims, feat_dims + 3 * e->n_feats);
+  for (auto& c : e->cache) { c.recs.clear(); c.next = 0; }      // launch records hold the old shapes / pointers
+  drop_graphs(e);
+  return 0;
+}
+
+// Launch op i through its cached record (building it on first use for these pointers).
+static int launch_cached(yl_engine* e, int i, const float* in, const unsigned char* in_u8, const float* res, const float* up, float* out,
+                         cudaStream_t st, int pdl) {
+  const yl_op& op = e->ops[i];
+  OpCache& oc = e->cache[i];
+  for (const OpRec& r : oc.recs)
+    if (r.in == in && r.in_u8 == in_u8 && r.out == out && r.res == res && r.up == up) {
+      ++g_tc_launches;
+      return r.kind == 1 ? tc_launch(r.tc, st, pdl) : stem2_launch(r.s2, st, pdl);
+    }
+  ConvParams p;
+  fill_params(p, op, e->d_blob, in, res, up, out, e->B, e->op_hin[i], e->op_win[i], e->op_hout[i], e->op_wout[i], e->op_hu[i], e->op_wu[i],
+              in_u8);
+  OpRec rec;
+  rec.in = in; rec.in_u8 = in_u8; rec.out = out; rec.res = res; rec.up = up;
+  if (op.kind == YL_OP_STEM2) {
+    if (!(op.w3_off >= 0 && !g_old_stem && stem2_supported(p)))
+      return run_stem2_unfused(op, p, e->d_blob, e->has_stem_tmp ? reinterpret_cast<float*>(e->arena + e->stem_tmp_off) : nullptr, e->sm_count, st);
+    rec.kind = 2;
+    if (int rc = stem2_prepare(p, e->d_blob + op.w3_off, e->sm_count, &rec.s2)) return rc;
+  } else {
+    const int mode = tc_mode_for(op, p, e->use_tc, e->op_hout[i], e->op_wout[i]);
+    if (mode < 0) return launch_simt(op, p, st);
+    rec.kind = 1;
+    if (int rc = tc_prepare(p, e->d_blob + op.wt_off, mode, e->sm_count, &rec.tc)) return rc;
+  }
+  ++g_prepares;
+  if (oc.recs.size() < 4) oc.recs.push_back(rec);
+  else { oc.recs[oc.next] = rec; oc.next = (oc.next + 1) % 4; }
+  ++g_tc_launches;
+  return rec.kind == 1 ? tc_launch(rec.tc, st, pdl) : stem2_launch(rec.s2, st, pdl);
+}
+
+struct CallArgs {
+  const float* x = nullptr;
+  const unsigned char* x_u8 = nullptr;
+  const float* const* feats = nullptr;
+  float* levels[MAX_LEVELS] = {};
+  // detect
+  int detect = 0, img_size = 0, max_det = 0, cap = 0;
+  float conf = 0.f;
+  double iou = 0.0;
+  float* boxes = nullptr; float* scores = nullptr; int64_t* classes = nullptr; int64_t* anchor_idx = nullptr;
+  int32_t* counts = nullptr; float* packed = nullptr;
+};
+
+static int enqueue_ops(yl_engine* e, const CallArgs& a, cudaStream_t st, cudaEvent_t* ev) {
+  if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[0], st));
+  auto bufptr = [&](int id) -> float* { return reinterpret_cast<float*>(e->arena + e->bufs[id].off); };
+  const int pdl = ev ? 0 : e->pdl;
+  for (size_t i = 0; i < e->ops.size(); ++i) {
+    const yl_op& op = e->ops[i];
+    const float* in = op.src == YL_SRC_INPUT ? a.x : op.src <= YL_SRC_FEATURE(0) ? a.feats[YL_FEATURE_INDEX(op.src)] : bufptr(op.src);
+    float* outp = op.dst >= 0 ? bufptr(op.dst) : a.levels[-op.dst - 1];
+    YL_REQUIRE(outp, "null level output pointer");
+    YL_REQUIRE(in || (op.src == YL_SRC_INPUT && a.x_u8), "null input pointer");
+    if (int rc = launch_cached(e, (int)i, in, op.src == YL_SRC_INPUT ? a.x_u8 : nullptr, op.res >= 0 ? bufptr(op.res) : nullptr,
+                               op.up >= 0 ? bufptr(op.up) : nullptr, outp, st, pdl))
+      return rc;
+    if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
+  }
+  if (a.detect) {
+    int32_t dims[MAX_LEVELS * 3];
+    const float* lv[MAX_LEVELS];
+    for (int l = 0; l < e->n_levels; ++l) {
+      dims[l * 3] = e->level_shape[l * 4]; dims[l * 3 + 1] = e->level_shape[l * 4 + 1]; dims[l * 3 + 2] = e->level_shape[l * 4 + 2];
+      lv[l] = a.levels[l];
+    }
+    return post_run(lv, dims, e->n_levels, e->B, e->level_shape[3], a.img_size, a.conf, a.iou, a.max_det, a.cap, a.boxes, a.scores,
+                    a.classes, a.anchor_idx, a.counts, a.packed, e->arena + e->post_scratch_off, e->post_scratch_bytes, st);
+  }
+  return 0;
+}
+
+static int run_call(yl_engine* e, const CallArgs& a, int B, int H, int W, const int32_t* feat_dims, cudaStream_t st, cudaEvent_t* ev) {
+  YL_REQUIRE(!a.x_u8 || (e->ops[0].kind == YL_OP_STEM2 && e->ops[0].src == YL_SRC_INPUT && e->ops[0].w3_off >= 0 && e->use_tc),
+             "this layer program has no uint8 image entry (fused stem kernel required)");
+  if (int rc = plan(e, B, H, W, feat_dims)) return rc;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (st != nullptr) { if (cudaStreamIsCapturing(st, &cs) != cudaSuccess) { cudaGetLastError(); cs = cudaStreamCaptureStatusNone; } }
+  if (!e->use_graph || ev || cs != cudaStreamCaptureStatusNone) return enqueue_ops(e, a, st, ev);
+
+  // ---- CUDA graph: one capture per distinct call, then replays
+  CallKey k;
+  memset(&k, 0, sizeof(k));
+  k.x = a.x; k.x_u8 = a.x_u8;
+  for (int f = 0; f < e->n_feats; ++f) k.feats[f] = a.feats[f];
+  for (int l = 0; l < e->n_levels; ++l) k.levels[l] = a.levels[l];
+  k.det[0] = a.boxes; k.det[1] = a.scores; k.det[2] = a.classes; k.det[3] = a.anchor_idx; k.det[4] = a.counts; k.det[5] = a.packed;
+  k.B = B; k.H = H; k.W = W; k.detect = a.detect; k.img_size = a.img_size; k.max_det = a.max_det; k.cap = a.cap;
+  k.use_tc = e->use_tc; k.pdl = e->pdl; k.conf = a.conf; k.iou = a.iou;
+  ++e->tick;
+  GraphRec* slot = nullptr;
+  for (auto& g : e->graphs)
+    if (memcmp(&g.key, &k, sizeof(k)) == 0) { slot = &g; break; }
+  if (slot && slot->exec) {
+    slot->last_use = e->tick;
+    ++g_graph_launches;
+    YL_CHECK_CUDA(cudaGraphLaunch(slot->exec, st));
+    return 0;
+  }
+  if (!slot) {
+    // first call with these pointers: run eagerly (this builds the launch records and sets the kernel attributes outside
+    // of any capture); the second call captures
+    GraphRec g;
+    g.key = k; g.last_use = e->tick;
+    if (e->graphs.size() >= 8) {          // evict the least recently used
+      size_t v = 0;
+      for (size_t i = 1; i < e->graphs.size(); ++i) if (e->graphs[i].last_use < e->graphs[v].last_use) v = i;
+      if (e->graphs[v].exec) cudaGraphExecDestroy(e->graphs[v].exec);
+      if (e->graphs[v].graph) cudaGraphDestroy(e->graphs[v].graph);
+      e->graphs[v] = g;
+    } else e->graphs.push_back(g);
+    return enqueue_ops(e, a, st, nullptr);
+  }
+  if (!e->cap_stream) YL_CHECK_CUDA(cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking));
+  // capture on an engine-owned stream (the caller's may be the legacy default stream, which cannot be captured)
+  YL_CHECK_CUDA(cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_ops(e, a, e->cap_stream, nullptr);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(e->cap_stream, &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+  YL_CHECK_CUDA(ce);
+  slot->graph = graph; slot->last_use = e->tick;
+  YL_CHECK_CUDA(cudaGraphInstantiate(&slot->exec, graph, 0));
+  ++g_graph_captures;
+  ++g_graph_launches;
+  YL_CHECK_CUDA(cudaGraphLaunch(slot->exec, st));
   return 0;
 }
 
@@ -173,6 +458,9 @@ long long yl_stat(const char* key) {
   if (!std::strcmp(key, "tc_launches")) return yl::g_tc_launches;
   if (!std::strcmp(key, "simt_launches")) return yl::g_simt_launches;
   if (!std::strcmp(key, "post_launches")) return yl::g_post_launches;
+  if (!std::strcmp(key, "graph_launches")) return yl::g_graph_launches;
+  if (!std::strcmp(key, "graph_captures")) return yl::g_graph_captures;
+  if (!std::strcmp(key, "prepares")) return yl::g_prepares;
   return -1;
 }
 int yl_abi_version(void) { return YL_ABI_VERSION; }
@@ -186,14 +474,16 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
                      int32_t n_levels, int32_t device, yl_engine** out) {
   using namespace yl;
   YL_REQUIRE(ops && n_ops > 0 && blob_host && blob_floats > 0 && out, "null/empty arguments");
-  YL_REQUIRE(n_buffers >= 1 && n_levels >= 1 && n_levels <= 8, "n_buffers >= 1, 1 <= n_levels <= 8");
+  YL_REQUIRE(n_buffers >= 1 && n_levels >= 1 && n_levels <= MAX_LEVELS, "n_buffers >= 1, 1 <= n_levels <= 8");
   int ndev = 0;
   YL_CHECK_CUDA(cudaGetDeviceCount(&ndev));
   YL_REQUIRE(device >= 0 && device < ndev, "no such CUDA device (this engine has no CPU fallback)");
-  YL_CHECK_CUDA(cudaSetDevice(device));
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(device) == 0, "cannot select the CUDA device");
   cudaDeviceProp prop;
   YL_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   YL_REQUIRE(prop.major == 10, "yololite_b200 is built for sm_100a (B200) only");
+  int n_feats = 0;
   for (int i = 0; i < n_ops; ++i) {
     const yl_op& op = ops[i];
     YL_REQUIRE(op.kind >= YL_OP_STEM && op.kind <= YL_OP_STEM2, "unknown op kind");
@@ -207,11 +497,16 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
     YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
     YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
     YL_REQUIRE((op.w_off & 3) == 0 && (op.b_off < 0 || (op.b_off & 3) == 0), "blob offsets must be 16-byte aligned");
+    if (op.src <= YL_SRC_FEATURE(0)) {
+      YL_REQUIRE(YL_FEATURE_INDEX(op.src) < MAX_FEATS && op.kind == YL_OP_CONV, "feature inputs: at most 8, read by YL_OP_CONV ops");
+      n_feats = std::max(n_feats, YL_FEATURE_INDEX(op.src) + 1);
+    }
   }
   yl_engine* e = new yl_engine();
   e->device = device;
   e->ops.assign(ops, ops + n_ops);
-  e->n_buffers = n_buffers; e->n_levels = n_levels; e->blob_floats = blob_floats;
+  e->cache.resize(n_ops);
+  e->n_buffers = n_buffers; e->n_levels = n_levels; e->blob_floats = blob_floats; e->n_feats = n_feats;
   e->sm_count = prop.multiProcessorCount;
   if (cudaMalloc(&e->d_blob, blob_floats * sizeof(float)) != cudaSuccess ||
       cudaMemcpy(e->d_blob, blob_host, blob_floats * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
@@ -226,7 +521,10 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
 
 int yl_engine_destroy(yl_engine* e) {
   if (!e) return 0;
-  cudaSetDevice(e->device);
+  yl::DeviceGuard dg;
+  dg.enter(e->device);
+  yl::drop_graphs(e);
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   if (e->arena) cudaFree(e->arena);
   if (e->d_blob) cudaFree(e->d_blob);
   delete e;
@@ -236,7 +534,14 @@ int yl_engine_destroy(yl_engine* e) {
 int yl_engine_set_option(yl_engine* e, const char* key, int32_t value) {
   using namespace yl;
   YL_REQUIRE(e && key, "null argument");
-  if (std::strcmp(key, "tensor_cores") == 0) { e->use_tc = value ? 1 : 0; return 0; }
+  if (std::strcmp(key, "tensor_cores") == 0) {
+    const int v = value ? 1 : 0;
+    if (v != e->use_tc) { for (auto& c : e->cache) { c.recs.clear(); c.next = 0; } }
+    e->use_tc = v;
+    return 0;
+  }
+  if (std::strcmp(key, "pdl") == 0) { e->pdl = value ? 1 : 0; return 0; }
+  if (std::strcmp(key, "graph") == 0) { e->use_graph = value ? 1 : 0; return 0; }
   YL_REQUIRE(false, "unknown engine option");
   return -1;
 }
@@ -266,57 +571,95 @@ int yl_run_op(const yl_op* op, const float* blob_dev, const float* in, const flo
 int yl_engine_plan(yl_engine* e, int32_t B, int32_t H, int32_t W, int32_t* shapes) {
   using namespace yl;
   YL_REQUIRE(e, "null engine");
-  YL_CHECK_CUDA(cudaSetDevice(e->device));
-  if (int rc = plan(e, B, H, W)) return rc;
+  YL_REQUIRE(e->n_feats == 0, "this layer program reads backbone features: use yl_engine_plan_features");
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
+  if (int rc = plan(e, B, H, W, nullptr)) return rc;
   if (shapes) std::memcpy(shapes, e->level_shape.data(), e->level_shape.size() * sizeof(int));
   return 0;
 }
 
-static int forward_impl(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
-                        void* stream, cudaEvent_t* ev, const unsigned char* x_u8 = nullptr) {
+int yl_engine_plan_features(yl_engine* e, int32_t B, const int32_t* feat_dims, int32_t n_feats, int32_t* shapes) {
   using namespace yl;
-  YL_REQUIRE(e && (x || x_u8) && level_out, "null argument");
-  YL_REQUIRE(!x_u8 || (e->ops[0].kind == YL_OP_STEM2 && e->ops[0].src == YL_SRC_INPUT && e->ops[0].w3_off >= 0 && e->use_tc),
-             "this layer program has no uint8 image entry (fused stem kernel required)");
-  YL_CHECK_CUDA(cudaSetDevice(e->device));
-  if (int rc = plan(e, B, H, W)) return rc;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[0], st));
-  auto bufptr = [&](int id) -> float* { return reinterpret_cast<float*>(e->arena + e->bufs[id].off); };
-  for (size_t i = 0; i < e->ops.size(); ++i) {
-    const yl_op& op = e->ops[i];
-    const float* in = op.src == YL_SRC_INPUT ? x : bufptr(op.src);
-    float* outp;
-    if (op.dst >= 0) outp = bufptr(op.dst);
-    else {
-      outp = level_out[-op.dst - 1];
-      YL_REQUIRE(outp, "null level output pointer");
-    }
-    int rc = run_op(op, e->d_blob, in, op.res >= 0 ? bufptr(op.res) : nullptr, op.up >= 0 ? bufptr(op.up) : nullptr, outp, B,
-                    e->op_hin[i], e->op_win[i], e->op_hout[i], e->op_wout[i], e->op_hu[i], e->op_wu[i], e->use_tc,
-                    e->sm_count, st, op.src == YL_SRC_INPUT ? x_u8 : nullptr);
-    if (rc) return rc;
-    if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
-  }
+  YL_REQUIRE(e && feat_dims, "null argument");
+  YL_REQUIRE(e->n_feats > 0 && n_feats == e->n_feats, "feature count does not match the layer program");
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
+  if (int rc = plan(e, B, 0, 0, feat_dims)) return rc;
+  if (shapes) std::memcpy(shapes, e->level_shape.data(), e->level_shape.size() * sizeof(int));
   return 0;
 }
 
+static int forward_entry(yl_engine* e, const float* x, const uint8_t* x_u8, int32_t B, int32_t H, int32_t W, float* const* level_out,
+                         void* stream, cudaEvent_t* ev) {
+  using namespace yl;
+  YL_REQUIRE(e && (x || x_u8) && level_out, "null argument");
+  YL_REQUIRE(e->n_feats == 0, "this layer program reads backbone features: use yl_forward_features");
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
+  CallArgs a;
+  a.x = x; a.x_u8 = x_u8;
+  for (int l = 0; l < e->n_levels; ++l) { a.levels[l] = level_out[l]; YL_REQUIRE(a.levels[l], "null level output pointer"); }
+  return run_call(e, a, B, H, W, nullptr, reinterpret_cast<cudaStream_t>(stream), ev);
+}
+
 int yl_forward(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out, void* stream) {
-  return forward_impl(e, x, B, H, W, level_out, stream, nullptr);
+  return forward_entry(e, x, nullptr, B, H, W, level_out, stream, nullptr);
 }
 
 int yl_forward_u8(yl_engine* e, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, float* const* level_out, void* stream) {
-  return forward_impl(e, nullptr, B, H, W, level_out, stream, nullptr, images_bgr);
+  return forward_entry(e, nullptr, images_bgr, B, H, W, level_out, stream, nullptr);
+}
+
+int yl_forward_features(yl_engine* e, const float* const* feats, const int32_t* feat_dims, int32_t n_feats, int32_t B,
+                        float* const* level_out, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(e && feats && feat_dims && level_out, "null argument");
+  YL_REQUIRE(e->n_feats > 0 && n_feats == e->n_feats, "feature count does not match the layer program");
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
+  CallArgs a;
+  a.feats = feats;
+  for (int f = 0; f < n_feats; ++f) YL_REQUIRE(feats[f] && (reinterpret_cast<uintptr_t>(feats[f]) & 15) == 0, "feature pointers must be non-null and 16-byte aligned");
+  for (int l = 0; l < e->n_levels; ++l) { a.levels[l] = level_out[l]; YL_REQUIRE(a.levels[l], "null level output pointer"); }
+  return run_call(e, a, B, 0, 0, feat_dims, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int yl_engine_detect(yl_engine* e, const float* x, const uint8_t* images_bgr, int32_t B, int32_t H, int32_t W, int32_t img_size,
+                     float conf, double iou, int32_t max_det_per_class, int32_t cap, float* boxes, float* scores, int64_t* classes,
+                     int64_t* anchor_idx, int32_t* counts, float* packed, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(e && ((x != nullptr) != (images_bgr != nullptr)), "pass exactly one of x (fp32 NCHW) and images_bgr (uint8 HWC)");
+  YL_REQUIRE(e->n_feats == 0, "this layer program reads backbone features");
+  YL_REQUIRE(cap >= 1 && (packed || (boxes && scores && classes && anchor_idx && counts)), "null output pointer");
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
+  if (int rc = plan(e, B, H, W, nullptr)) return rc;
+  CallArgs a;
+  a.x = x; a.x_u8 = images_bgr;
+  for (int l = 0; l < e->n_levels; ++l) a.levels[l] = reinterpret_cast<float*>(e->arena + e->level_off[l]);
+  a.detect = 1; a.img_size = img_size; a.conf = conf; a.iou = iou; a.max_det = max_det_per_class; a.cap = cap;
+  a.boxes = boxes; a.scores = scores; a.classes = classes; a.anchor_idx = anchor_idx; a.counts = counts; a.packed = packed;
+  return run_call(e, a, B, H, W, nullptr, reinterpret_cast<cudaStream_t>(stream), nullptr);
+}
+
+int yl_engine_levels(yl_engine* e, float** level_ptrs, int32_t* shapes) {
+  using namespace yl;
+  YL_REQUIRE(e && e->arena, "engine has no plan yet");
+  for (int l = 0; l < e->n_levels; ++l) if (level_ptrs) level_ptrs[l] = reinterpret_cast<float*>(e->arena + e->level_off[l]);
+  if (shapes) std::memcpy(shapes, e->level_shape.data(), e->level_shape.size() * sizeof(int));
+  return 0;
 }
 
 int yl_forward_profile(yl_engine* e, const float* x, int32_t B, int32_t H, int32_t W, float* const* level_out,
                        void* stream, float* op_ms, int32_t n_ops) {
   using namespace yl;
   YL_REQUIRE(e && op_ms && n_ops == (int)e->ops.size(), "op_ms must hold one float per op");
-  YL_CHECK_CUDA(cudaSetDevice(e->device));
+  DeviceGuard dg;
+  YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
   std::vector<cudaEvent_t> ev(n_ops + 1);
   for (auto& v : ev) YL_CHECK_CUDA(cudaEventCreate(&v));
-  int rc = forward_impl(e, x, B, H, W, level_out, stream, ev.data());
+  int rc = forward_entry(e, x, nullptr, B, H, W, level_out, stream, ev.data());
   if (rc == 0) {
     if (cudaEventSynchronize(ev[n_ops]) != cudaSuccess) { set_error("event sync failed"); rc = -2; }
     for (int i = 0; i < n_ops && rc == 0; ++i)
@@ -333,6 +676,8 @@ int yl_engine_read_buffer(yl_engine* e, int32_t buf, float* dst, int32_t* dims, 
   const BufShape& b = e->bufs[buf];
   if (dims) { dims[0] = b.H; dims[1] = b.W; dims[2] = b.C; }
   if (dst) {
+    DeviceGuard dg;
+    YL_REQUIRE(dg.enter(e->device) == 0, "cannot select the engine's device");
     YL_CHECK_CUDA(cudaMemcpyAsync(dst, e->arena + b.off, (size_t)e->B * b.H * b.W * b.C * sizeof(float),
                                   cudaMemcpyDeviceToDevice, reinterpret_cast<cudaStream_t>(stream)));
   }

@@ -1,0 +1,111 @@
+// Launch records of the tcgen05 kernels: everything a launch needs (kernel parameters, tensor maps, grid, shared memory) is
+// computed ONCE per (op, shape, pointers) by *_prepare and replayed by *_launch, so yl_forward does no planning, no
+// cuTensorMapEncodeTiled and no allocation per call.  Also: programmatic dependent launch (PDL) helpers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <utility>
+
+#include "common.cuh"
+
+namespace yl {
+
+// ---- PDL (griddepcontrol): a kernel launched with the programmatic-stream-serialization attribute may start while the previous
+// kernel in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation, weight copies: constant
+// data only) overlaps the previous kernel's tail.  Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1u : 0u;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies per DEVICE: run `set` once for every device a launch is prepared on.
+template <typename F>
+inline int once_per_device(bool* done /*[64]*/, std::mutex& m, F set) {
+  int dev = 0;
+  YL_CHECK_CUDA(cudaGetDevice(&dev));
+  YL_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+  std::lock_guard<std::mutex> lk(m);
+  if (!done[dev]) {
+    if (int rc = set()) return rc;
+    done[dev] = true;
+  }
+  return 0;
+}
+
+struct TcParams {
+  ConvParams c;
+  const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
+  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise KSxKS -> pointwise, 3 stem -> 3x3 s2 (older tf32 kernel)
+  int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
+  int Hs, Ws;           // MODE 3: stem output size
+  int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
+  int halo_slots;       // MODE 2: halo ring depth
+  int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
+  int dw_stride;        // MODE 2: stride of the depthwise stage (1 or 2); the output tile is tile_w x tile_h, the halo covers
+                        // (tile - 1) * stride + KS input pixels per dimension
+  int halo_tx;          // MODE 1 + TMA: exact bytes of one halo box (the slot stride halo_bytes is rounded up to 128)
+  int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
+  int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
+  int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
+  int stg_stride;       // bytes of epilogue staging per warp (TC_STG_BYTES; the smem-starved MODE 3 packs them at 4608)
+  int tma_out;          // epilogue writes each warp's 32 x 32 block through a swizzled staging tile + TMA tensor store
+  int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
+  int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
+                        // streamed from L2 into the A stage's own W slot with cp.async.bulk
+  int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
+  int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
+  long long M;
+  int num_tiles;
+};
+
+struct TcLaunch {
+  TcParams p;
+  CUtensorMap tmap, omap;
+  dim3 grid;
+  size_t smem;
+  int ks;              // depthwise kernel size of MODE 2
+};
+int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, TcLaunch* L);
+int tc_launch(const TcLaunch& L, cudaStream_t st, int pdl);
+
+struct Stem2Params {
+  const float* __restrict__ in;        // [B,3,H,W] fp32 NCHW
+  const float* __restrict__ wimg;      // bf16 image: [9 taps][3 splits][N2][32] SW64 | [3 splits][32][32] SW64
+  const float* __restrict__ bias2;     // [Cout]
+  float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
+  int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
+  int tiles_x, tiles_y, num_tiles;
+  int a1_stages;                       // stem operand stages: 2, or 1 when the 32-channel conv2 weights leave no room for two
+  const unsigned char* __restrict__ in_u8;   // image mode: [B,H,W,3] uint8 BGR (the reference's cv2 image, tools/infer.py:436-453) read
+                                       // directly: (u/255 - mean)/std is affine in the integer u, so it is folded into the stem
+                                       // weights; u8 values are exact in ONE bf16 -> GEMM1 takes one instruction per k-step
+  const float* __restrict__ pw;        // optional fused pointwise conv after conv2 (timm blocks.0.1): [Cout][Cout] weights (k-major,
+                                       // BN folded) followed by Cout biases; needs Cout == N2 == 16.  nullptr: none
+  int pw_act;
+};
+
+struct Stem2Launch {
+  Stem2Params p;
+  CUtensorMap tmap;
+  int grid;
+  size_t smem;
+};
+int stem2_prepare(const ConvParams& c, const float* wimg, int sm_count, Stem2Launch* L);
+int stem2_launch(const Stem2Launch& L, cudaStream_t st, int pdl);
+
+}  // namespace yl

@@ -15,7 +15,10 @@
 // finishes an image last, found with a per-image ticket): sort the keys (class asc, score desc, anchor asc)
 // in shared memory, run greedy NMS per class segment (one warp per segment, boxes and dead-bits in
 // registers for segments <= 128), compact the survivors into the fixed-capacity output.
+#include <mutex>
+
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace yl {
 
@@ -47,7 +50,9 @@ struct PostParams {
   float4* cbox;           // [B][N] decoded box by anchor index
   unsigned char* gflags;  // [B][N]
   // outputs
-  float* boxes; float* scores; long long* classes; long long* anchor_idx; int* counts;
+  float* boxes; float* scores; long long* classes; long long* anchor_idx; int* counts;   // each may be null when `packed` is set
+  float* packed;          // optional [B][cap + 1][6] fp32: row 0 = (count, overflow flag, total kept, 0, 0, 0), rows 1.. =
+                          // (x1, y1, x2, y2, score, class): ONE buffer a multi-GPU gather can ship as it is
 };
 
 __device__ __forceinline__ float sigmoid_exact(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
@@ -335,17 +340,28 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
         const unsigned long long key = keys[pos];
         const int n = key_anchor(key);
         const size_t q = (size_t)b * p.cap + o;
-        reinterpret_cast<float4*>(p.boxes)[q] = __ldcg(cbox + n);
-        p.scores[q] = key_score(key);
-        p.classes[q] = key_cls(key);
-        p.anchor_idx[q] = n;
+        const float4 bx = __ldcg(cbox + n);
+        if (p.boxes) reinterpret_cast<float4*>(p.boxes)[q] = bx;
+        if (p.scores) p.scores[q] = key_score(key);
+        if (p.classes) p.classes[q] = key_cls(key);
+        if (p.anchor_idx) p.anchor_idx[q] = n;
+        if (p.packed) {
+          float* r = p.packed + ((size_t)b * (p.cap + 1) + 1 + o) * 6;      // 24-byte rows: 8-byte aligned
+          reinterpret_cast<float2*>(r)[0] = make_float2(bx.x, bx.y);
+          reinterpret_cast<float2*>(r)[1] = make_float2(bx.z, bx.w);
+          reinterpret_cast<float2*>(r)[2] = make_float2(key_score(key), (float)key_cls(key));
+        }
       }
     }
     running += s_total;
     __syncthreads();
   }
   if (tid == 0) {
-    p.counts[b] = running <= p.cap ? running : (p.cap | (1 << 30));
+    if (p.counts) p.counts[b] = running <= p.cap ? running : (p.cap | (1 << 30));
+    if (p.packed) {
+      float* h = p.packed + (size_t)b * (p.cap + 1) * 6;
+      h[0] = (float)min(running, p.cap); h[1] = running > p.cap ? 1.f : 0.f; h[2] = (float)running; h[3] = 0.f; h[4] = 0.f; h[5] = 0.f;
+    }
     // self-clean the tickets so the scratch can be reused by the next launch without a memset
     p.count[b] = 0;
     p.done[b] = 0;
@@ -418,21 +434,37 @@ extern "C" size_t yl_postprocess_scratch_bytes(int32_t B, int64_t N) {
          yl::align_up(bn * 16, 256) + yl::align_up(bn, 256);
 }
 
-extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels,
-                              int32_t B, int32_t D, int32_t img_size, float conf, double iou,
-                              int32_t max_det_per_class, int32_t cap, float* boxes, float* scores,
-                              int64_t* classes, int64_t* anchor_idx, int32_t* counts, void* scratch,
-                              size_t scratch_bytes, void* stream) {
-  using namespace yl;
+namespace yl {
+
+// the device that owns `ptr` becomes current for the lifetime of the guard (postprocess / decode / preprocess take raw pointers
+// and no engine, so the device comes from the memory itself); the caller's device is restored afterwards
+struct PtrDeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  int enter(const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (at.type != cudaMemoryTypeDevice && at.type != cudaMemoryTypeManaged) return 0;
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (prev != at.device) { if (cudaSetDevice(at.device) != cudaSuccess) { cudaGetLastError(); return -2; } changed = true; }
+    return 0;
+  }
+  ~PtrDeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
+int post_run(const float* const* level_logits, const int32_t* level_dims, int n_levels, int B, int D, int img_size, float conf, double iou,
+             int max_det_per_class, int cap, float* boxes, float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts,
+             float* packed, void* scratch, size_t scratch_bytes, cudaStream_t st) {
   PostParams p{};
   if (int rc = fill_levels(p, level_logits, level_dims, n_levels, B, D, img_size)) return rc;
-  YL_REQUIRE(boxes && scores && classes && anchor_idx && counts && scratch, "null output/scratch pointer");
+  YL_REQUIRE(scratch && (packed || (boxes && scores && classes && anchor_idx && counts)), "null output/scratch pointer");
   YL_REQUIRE(cap >= 1, "cap >= 1");
   YL_REQUIRE(scratch_bytes >= yl_postprocess_scratch_bytes(B, p.N), "scratch too small");
   YL_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 255) == 0, "scratch must be 256-byte aligned");
+  YL_REQUIRE(!packed || (reinterpret_cast<uintptr_t>(packed) & 7) == 0, "packed output must be 8-byte aligned");
   p.conf = conf; p.iou = iou; p.max_det = max_det_per_class; p.cap = cap;
   p.boxes = boxes; p.scores = scores; p.classes = reinterpret_cast<long long*>(classes);
-  p.anchor_idx = reinterpret_cast<long long*>(anchor_idx); p.counts = counts;
+  p.anchor_idx = reinterpret_cast<long long*>(anchor_idx); p.counts = counts; p.packed = packed;
   unsigned char* s = reinterpret_cast<unsigned char*>(scratch);
   const size_t bn = (size_t)B * p.N;
   p.count = reinterpret_cast<int*>(s); p.done = p.count + B;
@@ -441,7 +473,6 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
   p.keys2 = reinterpret_cast<unsigned long long*>(s); s += align_up(bn * 8, 256);
   p.cbox = reinterpret_cast<float4*>(s); s += align_up(bn * 16, 256);
   p.gflags = s;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   YL_CHECK_CUDA(cudaMemsetAsync(p.count, 0, 2 * (size_t)B * sizeof(int), st));
   p.direct = conf >= 0.05f ? 1 : 0;
   p.smem_keys = p.direct ? POST_SMEM_KEYS / 2 : POST_SMEM_KEYS;
@@ -449,10 +480,17 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
   const size_t sort_bytes = (size_t)p.smem_keys * 9;
   const size_t smem = (tile_bytes > sort_bytes ? tile_bytes : sort_bytes) + 16;
   YL_REQUIRE(smem <= 200 * 1024, "5+C too large for the shared-memory tile (C <= 195)");
-  static thread_local size_t smem_set = 0;
-  if (smem > smem_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
+  {   // the dynamic shared memory limit is a per-device function attribute
+    static size_t smem_set[64];
+    static std::mutex mtx;
+    int dev = 0;
+    YL_CHECK_CUDA(cudaGetDevice(&dev));
+    YL_REQUIRE(dev >= 0 && dev < 64, "device index out of range");
+    std::lock_guard<std::mutex> lk(mtx);
+    if (smem > smem_set[dev]) {
+      YL_CHECK_CUDA(cudaFuncSetAttribute(post_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set[dev] = smem;
+    }
   }
   const unsigned grid = (unsigned)B * (unsigned)p.tile_off[n_levels];
   ++g_post_launches;
@@ -461,12 +499,39 @@ extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* l
   return 0;
 }
 
+}  // namespace yl
+
+extern "C" int yl_postprocess_ex(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels, int32_t B, int32_t D,
+                                 int32_t img_size, float conf, double iou, int32_t max_det_per_class, int32_t cap, float* boxes,
+                                 float* scores, int64_t* classes, int64_t* anchor_idx, int32_t* counts, float* packed, void* scratch,
+                                 size_t scratch_bytes, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(level_logits && level_dims && scratch, "null argument");
+  PtrDeviceGuard dg;
+  YL_REQUIRE(dg.enter(scratch) == 0, "cannot select the device that owns the scratch buffer");
+  return post_run(level_logits, level_dims, n_levels, B, D, img_size, conf, iou, max_det_per_class, cap, boxes, scores, classes,
+                  anchor_idx, counts, packed, scratch, scratch_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int yl_postprocess(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels,
+                              int32_t B, int32_t D, int32_t img_size, float conf, double iou,
+                              int32_t max_det_per_class, int32_t cap, float* boxes, float* scores,
+                              int64_t* classes, int64_t* anchor_idx, int32_t* counts, void* scratch,
+                              size_t scratch_bytes, void* stream) {
+  using namespace yl;
+  YL_REQUIRE(boxes && scores && classes && anchor_idx && counts && scratch, "null output/scratch pointer");
+  return yl_postprocess_ex(level_logits, level_dims, n_levels, B, D, img_size, conf, iou, max_det_per_class, cap, boxes, scores,
+                           classes, anchor_idx, counts, nullptr, scratch, scratch_bytes, stream);
+}
+
 extern "C" int yl_decode(const float* const* level_logits, const int32_t* level_dims, int32_t n_levels, int32_t B,
                          int32_t D, int32_t img_size, float* box, float* obj, float* cls, void* stream) {
   using namespace yl;
   PostParams p{};
   if (int rc = fill_levels(p, level_logits, level_dims, n_levels, B, D, img_size)) return rc;
   YL_REQUIRE(box && obj && (cls || D == 5), "null output pointer");
+  PtrDeviceGuard dg;
+  YL_REQUIRE(dg.enter(box) == 0, "cannot select the device that owns the output");
   const long long total = (long long)B * p.N * D;
   decode_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p, box, obj, cls);
   YL_CHECK_CUDA(cudaGetLastError());

@@ -26,7 +26,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace yl {
 
@@ -48,21 +51,6 @@ constexpr uint32_t S2_ACC1_COLS = 96, S2_ACC2_COL = S2_ACC1_RING * S2_ACC1_COLS,
 // parity planes (py, px): pixel offsets inside one split, pitch 9 (px = 0) or 8 (px = 1)
 __host__ __device__ constexpr int s2_plane_off(int py, int px) { return py ? (px ? 433 : 289) : (px ? 153 : 0); }
 
-struct Stem2Params {
-  const float* __restrict__ in;        // [B,3,H,W] fp32 NCHW
-  const float* __restrict__ wimg;      // bf16 image: [9 taps][3 splits][N2][32] SW64 | [3 splits][32][32] SW64
-  const float* __restrict__ bias2;     // [Cout]
-  float* __restrict__ out;             // [B,Ho,Wo,Cout] NHWC
-  int B, H, W, Hs, Ws, Ho, Wo, Cout, N2, act;
-  int tiles_x, tiles_y, num_tiles;
-  int a1_stages;                       // stem operand stages: 2, or 1 when the 32-channel conv2 weights leave no room for two
-  const unsigned char* __restrict__ in_u8;   // image mode: [B,H,W,3] uint8 BGR (the reference's cv2 image, tools/infer.py:436-453) read
-                                       // directly: (u/255 - mean)/std is affine in the integer u, so it is folded into the stem
-                                       // weights; u8 values are exact in ONE bf16 -> GEMM1 takes one instruction per k-step
-  const float* __restrict__ pw;        // optional fused pointwise conv after conv2 (timm blocks.0.1): [Cout][Cout] weights (k-major,
-                                       // BN folded) followed by Cout biases; needs Cout == N2 == 16.  nullptr: none
-  int pw_act;
-};
 
 namespace s2 {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -135,6 +123,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   // ---- shared memory carve-up
   const int w2_bytes = 27 * p.N2 * 64;                              // conv2 weights: 3 splits x 9 taps x N2 rows x 64 B
@@ -186,6 +175,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
   const int per_img = p.tiles_x * p.tiles_y;
+  pdl_wait();      // the prologue above read only weights; the network input / output buffers are touched from here on
   // TMEM columns: stem ring slot r: [96r, 96r + 96) = main | corr | corr (32 each); conv2 buffer b: 288 + 96b + {0, N2, 2*N2}
   constexpr uint32_t ACC2_COL = S2_ACC2_COL;
 
@@ -561,8 +551,9 @@ bool stem2_supported(const ConvParams& c) {
 }
 
 // c: geometry of the SECOND conv as set up by engine.cu for YL_OP_STEM2 (Hin/Win = network input size, Hout/Wout = conv2 output)
-int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st) {
-  Stem2Params p{};
+int stem2_prepare(const ConvParams& c, const float* wimg, int sm_count, Stem2Launch* L) {
+  Stem2Params& p = L->p;
+  p = Stem2Params{};
   p.in = c.in; p.in_u8 = c.in_u8; p.wimg = wimg; p.bias2 = c.bias; p.out = c.out;
   p.B = c.B; p.H = c.Hin; p.W = c.Win;
   p.Hs = (c.Hin + 2 - 3) / 2 + 1; p.Ws = (c.Win + 2 - 3) / 2 + 1;
@@ -577,14 +568,20 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
   p.num_tiles = (int)nt;
   p.a1_stages = stem2_a1_stages(p.N2);
   const size_t smem = stem2_smem_bytes(p.N2, p.a1_stages);
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  {
+    static bool done[64];
+    static std::mutex mtx;
+    if (int rc = once_per_device(done, mtx, []() -> int {
+          YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          YL_CHECK_CUDA(cudaFuncSetAttribute(stem2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          return 0;
+        }))
+      return rc;
   }
   int gx = sm_count < p.num_tiles ? sm_count : p.num_tiles;
-  CUtensorMap tmap;
+  L->grid = gx;
+  L->smem = smem;
+  CUtensorMap& tmap = L->tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (!p.in_u8) {
     const unsigned long long dims[3] = {(unsigned long long)p.W, (unsigned long long)p.H, (unsigned long long)p.B * 3};
@@ -592,10 +589,21 @@ int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStrea
     const unsigned int box[3] = {(unsigned)S2_PP, (unsigned)S2_PR, 3};
     if (int rc = make_tmap_f32(&tmap, p.in, 3, dims, strides, box, false)) return rc;
   }
-  if (p.a1_stages == 2) stem2_kernel<2><<<gx, S2_THREADS, smem, st>>>(p, tmap);
-  else stem2_kernel<1><<<gx, S2_THREADS, smem, st>>>(p, tmap);
-  YL_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int stem2_launch(const Stem2Launch& L, cudaStream_t st, int pdl) {
+  cudaError_t e;
+  if (L.p.a1_stages == 2) e = launch_ex(stem2_kernel<2>, dim3(L.grid), S2_THREADS, L.smem, st, pdl, L.p, L.tmap);
+  else e = launch_ex(stem2_kernel<1>, dim3(L.grid), S2_THREADS, L.smem, st, pdl, L.p, L.tmap);
+  YL_CHECK_CUDA(e);
+  return 0;
+}
+
+int launch_stem2(const ConvParams& c, const float* wimg, int sm_count, cudaStream_t st) {
+  Stem2Launch L;
+  if (int rc = stem2_prepare(c, wimg, sm_count, &L)) return rc;
+  return stem2_launch(L, st, 0);
 }
 
 }  // namespace yl

@@ -24,7 +24,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
+
 #include "common.cuh"
+#include "launch.cuh"
 
 namespace yl {
 
@@ -50,31 +53,6 @@ constexpr int TC_STG_BYTES = 5120;                    // per epilogue warp: the 
                                                       // SWIZZLE_128B tile a TMA store reads; 1024 B aligned
 constexpr int TC_AUX_BYTES = 256 + 512 + 4 * TC_STG_BYTES;      // barriers + tmem slot, bias vector, epilogue staging (one group)
 
-struct TcParams {
-  ConvParams c;
-  const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
-  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise KSxKS -> pointwise, 3 stem -> 3x3 s2 (older tf32 kernel)
-  int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
-  int Hs, Ws;           // MODE 3: stem output size
-  int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
-  int halo_slots;       // MODE 2: halo ring depth
-  int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
-  int dw_stride;        // MODE 2: stride of the depthwise stage (1 or 2); the output tile is tile_w x tile_h, the halo covers
-                        // (tile - 1) * stride + KS input pixels per dimension
-  int halo_tx;          // MODE 1 + TMA: exact bytes of one halo box (the slot stride halo_bytes is rounded up to 128)
-  int halo_w, halo_pix, halo_bytes;   // MODE 2: (tile_w + KS - 1) x (tile_h + KS - 1) input pixels, 128 B per pixel and K-slab
-  int prod_warps;       // producer warps (8; 4 when MODE 0 runs with TMA-loaded A tiles and two epilogue groups)
-  int epi2;             // MODE 0 + TMA: warps 4-7 form a second epilogue group; group g drains TMEM accumulator g (every other tile)
-  int stg_stride;       // bytes of epilogue staging per warp (TC_STG_BYTES; the smem-starved MODE 3 packs them at 4608)
-  int tma_out;          // epilogue writes each warp's 32 x 32 block through a swizzled staging tile + TMA tensor store
-  int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
-  int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
-                        // streamed from L2 into the A stage's own W slot with cp.async.bulk
-  int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
-  int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
-  long long M;
-  int num_tiles;
-};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -200,6 +178,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvParams& c = p.c;
   const int M = (int)p.M;
+  pdl_launch_dependents();      // the next kernel's prologue may overlap this kernel (it waits for our completion before reading)
 
   // ---- shared memory carve-up (all slabs 1024 B aligned)
   const uint32_t w_slab_bytes = (uint32_t)p.Nc * 128u;
@@ -294,6 +273,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
+  // everything above touched only constant data (weights, biases) and this CTA's shared memory / TMEM: with PDL it overlapped
+  // the previous kernel's tail.  From here on activations written by earlier kernels are read.
+  pdl_wait();
 
   if (warp < p.prod_warps) {
     // =============================== producers ===============================
@@ -1403,8 +1385,9 @@ static int make_a_tmap(CUtensorMap* tm, const float* in, long long M, int C) {
   return 0;
 }
 
-int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st) {
-  TcParams p{};
+int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, TcLaunch* L) {
+  TcParams& p = L->p;
+  p = TcParams{};
   p.c = c;
   p.wimg = wimg;
   p.mode = mode;
@@ -1479,20 +1462,26 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   if (mode == 3) { YL_REQUIRE(p.Nc <= 32, "fused stem kernel: N chunk <= 32"); cols = 128; }
   p.tmem_cols = cols;
   const size_t smem = smem_override ? smem_override : pl.smem;
-  static thread_local bool attr_set = false;
-  if (!attr_set) {
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+  {
+    static bool done[64];
+    static std::mutex mtx;
+    if (int rc = once_per_device(done, mtx, []() -> int {
+          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          return 0;
+        }))
+      return rc;
   }
   int gx = sm_count / p.nchunks;
   if (gx < 1) gx = 1;
   if (gx > p.num_tiles) gx = p.num_tiles;
-  dim3 grid(gx, p.nchunks);
-  CUtensorMap tmap;
+  L->grid = dim3(gx, p.nchunks);
+  L->smem = smem;
+  L->ks = c.KS;
+  CUtensorMap& tmap = L->tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (tma_a) {
     if (int rc = make_a_tmap(&tmap, c.in, p.M, c.Cin)) return rc;
@@ -1510,7 +1499,7 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
   }
   // output tensor map for the TMA-store epilogue: plain vector epilogue (N % 4 == 0, no head layout), no residual / upsample
   // source, every 32-column block inside this CTA's chunk, and in the spatial modes a tile width that divides 32
-  CUtensorMap omap;
+  CUtensorMap& omap = L->omap;
   memset(&omap, 0, sizeof(omap));
   static const int tmaout_env = [] { const char* e = getenv("YL_TC_TMAOUT"); return e ? atoi(e) : 1; }();
   const bool spatial = mode == 2 || (mode == 1 && p.tma_a);
@@ -1531,13 +1520,25 @@ int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_coun
     if (rc) return rc;
     p.tma_out = 1;
   }
-  if (mode == 0) tc_conv_kernel<0, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
-  else if (mode == 1) tc_conv_kernel<1, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
-  else if (mode == 2 && c.KS == 3) tc_conv_kernel<2, 3><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
-  else if (mode == 2) tc_conv_kernel<2, 5><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
-  else tc_conv_kernel<3, 0><<<grid, TC_THREADS, smem, st>>>(p, tmap, omap);
-  YL_CHECK_CUDA(cudaGetLastError());
   return 0;
+}
+
+int tc_launch(const TcLaunch& L, cudaStream_t st, int pdl) {
+  const int mode = L.p.mode;
+  cudaError_t e;
+  if (mode == 0) e = launch_ex(tc_conv_kernel<0, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  else if (mode == 1) e = launch_ex(tc_conv_kernel<1, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  else if (mode == 2 && L.ks == 3) e = launch_ex(tc_conv_kernel<2, 3>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  else if (mode == 2) e = launch_ex(tc_conv_kernel<2, 5>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  else e = launch_ex(tc_conv_kernel<3, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  YL_CHECK_CUDA(e);
+  return 0;
+}
+
+int launch_tc_conv(const ConvParams& c, const float* wimg, int mode, int sm_count, cudaStream_t st) {
+  TcLaunch L;
+  if (int rc = tc_prepare(c, wimg, mode, sm_count, &L)) return rc;
+  return tc_launch(L, st, 0);
 }
 
 }  // namespace yl

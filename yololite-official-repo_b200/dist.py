@@ -32,7 +32,8 @@ def pack_detections(boxes: torch.Tensor, scores: torch.Tensor, classes: torch.Te
 
 def gather_detections(packed: torch.Tensor, counts: torch.Tensor, group=None, out: torch.Tensor = None,
                       out_counts: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
-    """All-gather equal-sized shards: packed [b,cap,6] -> [world*b,cap,6], counts [b] i32 -> [world*b] (rank order)."""
+    """All-gather equal-sized shards: packed [b,cap,6] -> [world*b,cap,6], counts [b] i32 -> [world*b] (rank order).
+    Two collectives; `gather_packed` below ships the kernel-written payload (counts in its header rows) in ONE."""
     world = dist.get_world_size(group)
     if out is None:
         out = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
@@ -41,6 +42,16 @@ def gather_detections(packed: torch.Tensor, counts: torch.Tensor, group=None, ou
     dist.all_gather_into_tensor(out, packed.contiguous(), group=group)
     dist.all_gather_into_tensor(out_counts, counts.contiguous(), group=group)
     return out, out_counts
+
+
+def gather_packed(packed: torch.Tensor, group=None, out: torch.Tensor = None, async_op: bool = False):
+    """The path's one exchange: ONE all-gather of the [b, cap+1, 6] payload the postprocess kernel
+    wrote itself (row 0 of every image = count / overflow flag / K).  -> ([world*b, cap+1, 6] in rank order, work handle)."""
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * packed.shape[0],) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    work = dist.all_gather_into_tensor(out, packed, group=group, async_op=async_op)
+    return out, work
 
 
 def unpack_detections(packed: torch.Tensor, counts: torch.Tensor) -> List[Dict[str, torch.Tensor]]:

@@ -83,13 +83,16 @@ def preprocess_batch(images_u8: torch.Tensor, img_size: int, out: Optional[torch
 class YoloLite:
     """`YoloLite(weights).predict(source)` -> list of result dicts (README.md:22-42)."""
 
-    def __init__(self, weights: str, device="cuda:0"):
+    def __init__(self, weights: str, device="cuda:0", graph: bool = True):
         self.model, self.names, self.img_size = load_model_names_imgsize_from_ckpt(weights, torch.device(device))
+        self.model.set_option("graph", 1 if graph else 0)
         self.device = torch.device(device)
         self._post = PostProcessor()
 
     def predict(self, source, device=None, draw: bool = False, conf: float = 0.4, iou: float = 0.5, max_det: int = 300,
                 img_size: int = 0) -> List[dict]:
+        """max_det is the PER-CLASS cap (`keep[:max_det]` inside the class loop of tools/infer.py:134-152,476-493); the reference
+        CLI always uses 300 there whatever its --max_det flag says, which is this default."""
         import cv2
         if device is not None and torch.device(device).type != "cuda":
             raise RuntimeError("yololite_b200 has no CPU path (device must be a CUDA device)")
@@ -107,8 +110,14 @@ class YoloLite:
             for s in source:
                 if isinstance(s, np.ndarray):
                     paths.append(None); imgs.append(s)
-                else:
-                    paths.append(str(s)); imgs.append(cv2.imread(str(s)))
+                    continue
+                im = cv2.imread(str(s))
+                if im is None:                          # tools/infer.py:437-440: warn and skip unreadable images
+                    print(f"⚠️  Kunde inte läsa {s}")
+                    continue
+                paths.append(str(s)); imgs.append(im)
+            if not imgs:
+                return []
         x, geo = preprocess(imgs, S, self.device)
         torch.cuda.synchronize(self.device)
         t1 = time.perf_counter()
@@ -132,18 +141,32 @@ class YoloLite:
     def predict_batch(self, images_u8: torch.Tensor, conf: float = 0.4, iou: float = 0.5, max_det: int = 300, img_size: int = 0,
                       cap: Optional[int] = None):
         """Batched device-side predict: uint8 [B,H,W,3] BGR (CUDA) -> Detections (fixed capacity, letterboxed coordinates)
-        + the letterbox geometry.  No host synchronisation; call `.to_list()` / `backmap` on the result when needed."""
+        + the letterbox geometry.  No host synchronisation; call `.to_list()` / `backmap` on the result when needed.  The
+        Detections alias buffers owned by this object: valid until the next predict_batch call with the same shape."""
+        from .post import Detections
         S = int(img_size) if img_size else self.img_size
         B, h0, w0 = images_u8.shape[0], images_u8.shape[1], images_u8.shape[2]
-        if h0 == S and w0 == S and self.model.supports_u8(S, S):
+        direct = h0 == S and w0 == S and self.model.supports_u8(S, S)
+        if direct:
             # no letterbox resize / padding needed: the stem kernel reads the uint8 image itself (normalisation folded in)
-            return self._post(self.model.forward_u8(images_u8), S, conf, iou, max_det, cap), (1.0, 0, 0, h0, w0)
-        key = (tuple(images_u8.shape), S)
-        if getattr(self, "_xbuf_key", None) != key:
-            self._xbuf = torch.empty((images_u8.shape[0], 3, S, S), device=images_u8.device, dtype=torch.float32)
-            self._xbuf_key = key
-        x, geo = preprocess_batch(images_u8, S, out=self._xbuf)
-        return self._post(self.model(x), S, conf, iou, max_det, cap), geo
+            x, geo = images_u8, (1.0, 0, 0, h0, w0)
+        else:
+            key = (tuple(images_u8.shape), S)
+            if getattr(self, "_xbuf_key", None) != key:
+                self._xbuf = torch.empty((images_u8.shape[0], 3, S, S), device=images_u8.device, dtype=torch.float32)
+                self._xbuf_key = key
+            x, geo = preprocess_batch(images_u8, S, out=self._xbuf)
+        cap = int(cap) if cap else 1024
+        okey = (B, cap, images_u8.device)
+        if getattr(self, "_obuf_key", None) != okey:
+            dev = images_u8.device
+            self._obuf = (torch.empty((B, cap, 4), device=dev), torch.empty((B, cap), device=dev),
+                          torch.empty((B, cap), device=dev, dtype=torch.int64), torch.empty((B, cap), device=dev, dtype=torch.int64),
+                          torch.zeros((B,), device=dev, dtype=torch.int32))
+            self._obuf_key = okey
+        # forward + postprocess as ONE C call (one CUDA graph launch once the engine has captured it)
+        bx, sc, cl, ix, cn = self.model.detect(x, S, conf, iou, max_det, cap, outputs=self._obuf)
+        return Detections(bx, sc, cl, ix, cn), geo
 
     def to_json(self, result: dict) -> dict:
         """The per-image JSON record tools/infer.py:540-549 writes."""

@@ -54,8 +54,9 @@ class ModelCfg:
     names: List[str]
 
 
-def parse_meta(meta: dict) -> ModelCfg:
-    """Same field resolution (and the same KeyError / ValueError behaviour) as tools/infer.py:34-77."""
+def parse_meta(meta: dict, from_features: bool = False) -> ModelCfg:
+    """Same field resolution (and the same KeyError / ValueError behaviour) as tools/infer.py:34-77.  from_features: the
+    layer program starts at the FPN (the backbone runs elsewhere), so any backbone name is accepted."""
     cfg = meta.get("config", {}) or {}
     mcfg = cfg.get("model", {}) or {}
     tcfg = cfg.get("training", {}) or {}
@@ -67,7 +68,7 @@ def parse_meta(meta: dict) -> ModelCfg:
     use_p2 = cfg["training"]["use_p2"]
     if arch not in ("yololitems", "yololitems_cpu"):
         raise ValueError(f"Okänd arch i meta/config: {arch}")
-    if backbone not in BACKBONES:
+    if backbone not in BACKBONES and not from_features:
         raise ValueError(f"backbone {backbone!r} has no sm_100a lowering yet (supported: {sorted(BACKBONES)})")
     levels = (("p2",) if use_p2 else ()) + ("p3", "p4", "p5") + (("p6",) if use_p6 else ())
     if len(apl) >= 3:
@@ -104,6 +105,7 @@ class Program:
     cfg: Optional[ModelCfg] = None
     n_buffers: int = 0
     vmap: Dict[int, int] = field(default_factory=dict)    # virtual id -> physical buffer id
+    feature_channels: Optional[List[int]] = None          # from_features programs: channels of the external inputs
 
     def add_blob(self, arr: np.ndarray) -> int:
         arr = np.ascontiguousarray(arr, dtype=np.float32).reshape(-1)      # float32 views (bf16 pairs) keep their bits
@@ -277,13 +279,17 @@ def _pad4(b: np.ndarray) -> np.ndarray:
 
 
 def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: bool = True,
-          tensor_cores: bool = True, fuse_stem: bool = True, fuse_uir: Optional[bool] = None, fuse_pw01: bool = True) -> Program:
-    """fuse_dwpw: DWConvBlock (FPN smooth / head trunk) as one op; fuse_uir (default = fuse_dwpw): the stride-1
+          tensor_cores: bool = True, fuse_stem: bool = True, fuse_uir: Optional[bool] = None, fuse_pw01: bool = True,
+          from_features: bool = False) -> Program:
+    """from_features: lower only the FPN + heads (model_v2.py:124-133,201-224 / :289-294,359-377); the program reads the backbone's
+    feature maps [c2,] c3, c4, c5 as external NHWC inputs (op.src = YL_SRC_FEATURE(i)), their channel counts are taken from
+    the lateral convs' weights, their reductions are assumed to be [4,] 8, 16, 32 (what every timm backbone the reference
+    configures returns).  fuse_dwpw: DWConvBlock (FPN smooth / head trunk) as one op; fuse_uir (default = fuse_dwpw): the stride-1
     depthwise convs of the backbone's UIR blocks ride in the producer stage of the pointwise conv that follows them
     (dw_start -> pw_exp, dw_mid -> pw_proj + residual), so their outputs never reach HBM."""
     if fuse_uir is None:
         fuse_uir = fuse_dwpw
-    cfg = parse_meta(meta)
+    cfg = parse_meta(meta, from_features)
     sd = _SD(state_dict)
     P = Program(cfg=cfg)
 
@@ -327,79 +333,85 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
         return emit(L.OP_DWPW, x, wp.shape[0], red, k=1, act=act, w=_gemm_w(wp), b=bp, res=res,
                     w2=np.transpose(wd, (2, 3, 1, 0)).reshape(k * k, -1), k2=k, b2=bdw, act2=act2, stride2=stride)
 
-    # ---------------- backbone
-    table, mult, stem_c = BACKBONES[cfg.backbone]
-    bb = "backbone."
-    first = table[0][0]
-    # the stem feature itself is never tapped (the FPN takes the last 3-4 taps), so conv_stem can be fused with
-    # blocks.0.0 when both are 3x3 s2 and the stem has 32 channels
-    fused_stem = bool(fuse_stem and tensor_cores and stem_c == 32 and first[0] == "cn" and first[1] == 3 and first[2] == 2)
-    pw_blob = None
-    if fused_stem:
-        ws = sd.get(bb + "conv_stem.weight")
-        s0, b0 = sd.bn(bb + "bn1")
-        ws = np.transpose(ws * s0[:, None, None, None], (2, 3, 1, 0)).reshape(27, stem_c)
-        key = bb + "blocks.0.0"
-        w1 = sd.get(key + ".conv.weight")
-        s1, b1 = sd.bn(key + ".bn1")
-        w1m = _gemm_w(w1 * s1[:, None, None, None])
-        # blocks.0.1 (1x1, same width, BN + ReLU) rides in the output epilogue of the fused kernel when conv2 has 16 channels
-        nxt01 = table[0][1] if len(table[0]) > 1 else None
-        c1 = int(w1.shape[0])
-        pw_blob = None
-        if fuse_pw01 and c1 == 16 and nxt01 is not None and nxt01[0] == "cn" and nxt01[1] == 1 and nxt01[2] == 1 and _round_ch(nxt01[3] * mult) == 16:
-            wq = sd.get(bb + "blocks.0.1.conv.weight")
-            sq, bq = sd.bn(bb + "blocks.0.1.bn1")
-            wq = (wq * sq[:, None, None, None])[:, :, 0, 0]                       # [n][k]
-            pw_blob = np.concatenate([wq.T.reshape(-1), bq.reshape(-1)])          # [k][n] then bias[n]
-        x = emit(L.OP_STEM2, None, c1, 4, k=3, stride=2, act=L.ACT_RELU, w=w1m, b2=pw_blob, act2=(L.ACT_RELU if pw_blob is not None else L.ACT_NONE),
-                 w3=stem2_image(w1m, int(w1.shape[0]), ws, b0) if int(w1.shape[0]) <= 32 else None,
-                 b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
-        feats = [_T(-1, stem_c, 2)]
-        red = 4
-    else:
-        x = conv_bn(None, bb + "conv_stem", bb + "bn1", 3, 2, L.ACT_RELU, 2)
-        feats = [x]
-        red = 2
-    for si, stage in enumerate(table):
-        for bi, spec in enumerate(stage):
-            key = f"{bb}blocks.{si}.{bi}"
-            if fused_stem and si == 0 and (bi == 0 or (bi == 1 and pw_blob is not None)):
-                pass
-            elif spec[0] == "cn":
-                _, k, s, c = spec
-                red *= s
-                x = conv_bn(x, key + ".conv", key + ".bn1", k, s, L.ACT_RELU, red)
-            else:
-                _, ks, km, s, e, c = spec
-                cout = _round_ch(c * mult)
-                skip = x if (x.C == cout and s == 1) else None
-                y = x
-                s_start = 1 if km else s
-                fuse_start = bool(ks and fuse_uir and s_start == 1 and x.C % 4 == 0)
-                fuse_mid = bool(km and fuse_uir and s in (1, 2))
-                if fuse_start:
-                    y = dw_pw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, L.ACT_NONE,
-                                 key + ".pw_exp.conv", key + ".pw_exp.bn", L.ACT_RELU, red)
-                else:
-                    if ks:
-                        y = dw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, s_start, L.ACT_NONE, red * s_start)
-                    y = conv_bn(y, key + ".pw_exp.conv", key + ".pw_exp.bn", 1, 1, L.ACT_RELU, y.red)
-                if fuse_mid:
-                    red *= s
-                    x = dw_pw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, L.ACT_RELU,
-                                 key + ".pw_proj.conv", key + ".pw_proj.bn", L.ACT_NONE, red, res=skip, stride=s)
-                else:
-                    if km:
-                        y = dw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, s, L.ACT_RELU, red * s)
-                    red *= s
-                    x = conv_bn(y, key + ".pw_proj.conv", key + ".pw_proj.bn", 1, 1, L.ACT_NONE, red, res=skip)
-            last_of_stage = bi == len(stage) - 1
-            nxt = table[si + 1][0] if si + 1 < len(table) else None
-            nxt_stride = None if nxt is None else (nxt[2] if nxt[0] == "cn" else nxt[3])
-            if last_of_stage and (nxt is None or nxt_stride > 1):
-                feats.append(x)
     take = 4 if cfg.use_p2 else 3
+    if from_features:
+        lat = (["lateral2"] if cfg.use_p2 else []) + ["lateral3", "lateral4", "lateral5"]
+        reds = [4, 8, 16, 32][-take:]
+        feats = [_T(L.src_feature(i), int(sd.get(nm + ".weight").shape[1]), r) for i, (nm, r) in enumerate(zip(lat, reds))]
+        P.feature_channels = [f.C for f in feats]
+    else:
+        # ---------------- backbone
+        table, mult, stem_c = BACKBONES[cfg.backbone]
+        bb = "backbone."
+        first = table[0][0]
+        # the stem feature itself is never tapped (the FPN takes the last 3-4 taps), so conv_stem can be fused with
+        # blocks.0.0 when both are 3x3 s2 and the stem has 32 channels
+        fused_stem = bool(fuse_stem and tensor_cores and stem_c == 32 and first[0] == "cn" and first[1] == 3 and first[2] == 2)
+        pw_blob = None
+        if fused_stem:
+            ws = sd.get(bb + "conv_stem.weight")
+            s0, b0 = sd.bn(bb + "bn1")
+            ws = np.transpose(ws * s0[:, None, None, None], (2, 3, 1, 0)).reshape(27, stem_c)
+            key = bb + "blocks.0.0"
+            w1 = sd.get(key + ".conv.weight")
+            s1, b1 = sd.bn(key + ".bn1")
+            w1m = _gemm_w(w1 * s1[:, None, None, None])
+            # blocks.0.1 (1x1, same width, BN + ReLU) rides in the output epilogue of the fused kernel when conv2 has 16 channels
+            nxt01 = table[0][1] if len(table[0]) > 1 else None
+            c1 = int(w1.shape[0])
+            pw_blob = None
+            if fuse_pw01 and c1 == 16 and nxt01 is not None and nxt01[0] == "cn" and nxt01[1] == 1 and nxt01[2] == 1 and _round_ch(nxt01[3] * mult) == 16:
+                wq = sd.get(bb + "blocks.0.1.conv.weight")
+                sq, bq = sd.bn(bb + "blocks.0.1.bn1")
+                wq = (wq * sq[:, None, None, None])[:, :, 0, 0]                       # [n][k]
+                pw_blob = np.concatenate([wq.T.reshape(-1), bq.reshape(-1)])          # [k][n] then bias[n]
+            x = emit(L.OP_STEM2, None, c1, 4, k=3, stride=2, act=L.ACT_RELU, w=w1m, b2=pw_blob, act2=(L.ACT_RELU if pw_blob is not None else L.ACT_NONE),
+                     w3=stem2_image(w1m, int(w1.shape[0]), ws, b0) if int(w1.shape[0]) <= 32 else None,
+                     b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
+            feats = [_T(-1, stem_c, 2)]
+            red = 4
+        else:
+            x = conv_bn(None, bb + "conv_stem", bb + "bn1", 3, 2, L.ACT_RELU, 2)
+            feats = [x]
+            red = 2
+        for si, stage in enumerate(table):
+            for bi, spec in enumerate(stage):
+                key = f"{bb}blocks.{si}.{bi}"
+                if fused_stem and si == 0 and (bi == 0 or (bi == 1 and pw_blob is not None)):
+                    pass
+                elif spec[0] == "cn":
+                    _, k, s, c = spec
+                    red *= s
+                    x = conv_bn(x, key + ".conv", key + ".bn1", k, s, L.ACT_RELU, red)
+                else:
+                    _, ks, km, s, e, c = spec
+                    cout = _round_ch(c * mult)
+                    skip = x if (x.C == cout and s == 1) else None
+                    y = x
+                    s_start = 1 if km else s
+                    fuse_start = bool(ks and fuse_uir and s_start == 1 and x.C % 4 == 0)
+                    fuse_mid = bool(km and fuse_uir and s in (1, 2))
+                    if fuse_start:
+                        y = dw_pw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, L.ACT_NONE,
+                                     key + ".pw_exp.conv", key + ".pw_exp.bn", L.ACT_RELU, red)
+                    else:
+                        if ks:
+                            y = dw_bn(y, key + ".dw_start.conv", key + ".dw_start.bn", ks, s_start, L.ACT_NONE, red * s_start)
+                        y = conv_bn(y, key + ".pw_exp.conv", key + ".pw_exp.bn", 1, 1, L.ACT_RELU, y.red)
+                    if fuse_mid:
+                        red *= s
+                        x = dw_pw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, L.ACT_RELU,
+                                     key + ".pw_proj.conv", key + ".pw_proj.bn", L.ACT_NONE, red, res=skip, stride=s)
+                    else:
+                        if km:
+                            y = dw_bn(y, key + ".dw_mid.conv", key + ".dw_mid.bn", km, s, L.ACT_RELU, red * s)
+                        red *= s
+                        x = conv_bn(y, key + ".pw_proj.conv", key + ".pw_proj.bn", 1, 1, L.ACT_NONE, red, res=skip)
+                last_of_stage = bi == len(stage) - 1
+                nxt = table[si + 1][0] if si + 1 < len(table) else None
+                nxt_stride = None if nxt is None else (nxt[2] if nxt[0] == "cn" else nxt[3])
+                if last_of_stage and (nxt is None or nxt_stride > 1):
+                    feats.append(x)
     feats = feats[-take:]
     P.strides = [f.red for f in feats] + ([feats[-1].red * 2] if cfg.use_p6 else [])
 
@@ -500,7 +512,7 @@ def _assign_buffers(P: Program, reuse: bool) -> None:
         for f in ("src", "res", "up", "dst"):
             if op[f] >= 0:
                 op[f] = P.vmap[op[f]]
-    P.taps = {k: P.vmap[v] for k, v in P.taps.items()}
+    P.taps = {k: P.vmap[v] for k, v in P.taps.items() if v >= 0}
 
 
 def to_c(P: Program):

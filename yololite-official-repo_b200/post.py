@@ -65,25 +65,43 @@ def decode_preds_anchorfree(preds_levels, img_size: int, center_mode: str = "v8"
 
 
 class Detections:
-    """Fixed-capacity device-side result of one postprocess launch."""
+    """Fixed-capacity device-side result of one postprocess launch.  The tensors belong to the PostProcessor / caller that
+    produced them and are overwritten by its next call; `to_list()` returns independent copies."""
 
     def __init__(self, boxes, scores, classes, index, counts):
         self.boxes, self.scores, self.classes, self.index, self.counts = boxes, scores, classes, index, counts
 
-    def to_list(self) -> List[Dict[str, torch.Tensor]]:
-        """Per image (boxes [K,4] f32, scores [K] f32, classes [K] i64, index [K] i64) sliced by the counts (one D2H sync)."""
+    def to_list(self, copy: bool = True) -> List[Dict[str, torch.Tensor]]:
+        """Per image (boxes [K,4] f32, scores [K] f32, classes [K] i64, index [K] i64) sliced by the counts (one D2H sync).
+        copy=True (default) clones the slices, like the fresh tensors the reference returns (tools/infer.py:476-493);
+        copy=False returns views that the next call on the same PostProcessor overwrites."""
         cnt = self.counts.cpu().tolist()
         out = []
         for b, c in enumerate(cnt):
             if c & OVERFLOW_BIT:
                 raise RuntimeError(f"image {b}: more detections than the output capacity {self.boxes.shape[1]}")
-            out.append({"boxes": self.boxes[b, :c], "scores": self.scores[b, :c], "classes": self.classes[b, :c],
-                        "index": self.index[b, :c]})
+            d = {"boxes": self.boxes[b, :c], "scores": self.scores[b, :c], "classes": self.classes[b, :c], "index": self.index[b, :c]}
+            out.append({k: v.clone() for k, v in d.items()} if copy else d)
         return out
 
 
+def unpack(packed: torch.Tensor) -> List[Dict[str, torch.Tensor]]:
+    """[B, cap+1, 6] payload written by the kernel (row 0 = count, overflow flag, K; rows 1.. = x1,y1,x2,y2,score,class)
+    -> per-image dicts like tools/infer.py produces (one D2H sync for the header rows)."""
+    head = packed[:, 0, :3].cpu()
+    res = []
+    for b in range(packed.shape[0]):
+        if head[b, 1] != 0:
+            raise RuntimeError(f"image {b}: {int(head[b, 2])} detections exceed the capacity {packed.shape[1] - 1}")
+        c = int(head[b, 0])
+        p = packed[b, 1:1 + c]
+        res.append({"boxes": p[:, :4].clone(), "scores": p[:, 4].clone(), "classes": p[:, 5].to(torch.int64)})
+    return res
+
+
 class PostProcessor:
-    """Owns the scratch + output buffers for a fixed (B, N, cap) so repeated calls allocate nothing."""
+    """Owns the scratch + output buffers for a fixed (B, N, cap) so repeated calls allocate nothing.  The returned Detections
+    alias those buffers: they are valid until the next call on this object (use one PostProcessor per stream / thread)."""
 
     def __init__(self):
         self._key = None
@@ -103,18 +121,25 @@ class PostProcessor:
 
     @torch.no_grad()
     def __call__(self, preds_levels, img_size: int, conf: float = 0.4, iou: float = 0.5, max_det: int = 300,
-                 cap: Optional[int] = None) -> Detections:
+                 cap: Optional[int] = None, packed: Optional[torch.Tensor] = None) -> Detections:
+        """max_det is the PER-CLASS cap of tools/infer.py:134-152 (`keep[:max_det]` inside the class loop; the reference CLI
+        always passes 300 there, its --max_det flag is not forwarded on this branch), 0 = unlimited (helpers.py:86-153).
+        packed: optional [B, cap+1, 6] fp32 tensor the kernel additionally fills (see `unpack`)."""
         lv = _levels5(preds_levels)
         B, D = lv[0].shape[0], lv[0].shape[-1]
         N = sum(p.shape[1] * p.shape[2] * p.shape[3] for p in lv)
         cap = int(cap) if cap else N
         dev = lv[0].device
         self._ensure(B, N, cap, dev)
+        if packed is not None and not (packed.is_cuda and packed.dtype == torch.float32 and tuple(packed.shape) == (B, cap + 1, 6)
+                                       and packed.is_contiguous()):
+            raise ValueError(f"packed must be a contiguous CUDA float32 tensor of shape {(B, cap + 1, 6)}")
         ptrs, dims = _level_args(lv)
-        L.check(L.lib().yl_postprocess(ptrs, dims, len(lv), B, D, int(img_size), float(conf), float(iou), int(max_det or 0),
-                                       cap, self.boxes.data_ptr(), self.scores.data_ptr(), self.classes.data_ptr(),
-                                       self.index.data_ptr(), self.counts.data_ptr(), self.scratch.data_ptr(),
-                                       self.scratch_bytes, _stream(dev)))
+        L.check(L.lib().yl_postprocess_ex(ptrs, dims, len(lv), B, D, int(img_size), float(conf), float(iou), int(max_det or 0),
+                                          cap, self.boxes.data_ptr(), self.scores.data_ptr(), self.classes.data_ptr(),
+                                          self.index.data_ptr(), self.counts.data_ptr(),
+                                          packed.data_ptr() if packed is not None else None, self.scratch.data_ptr(),
+                                          self.scratch_bytes, _stream(dev)))
         return Detections(self.boxes, self.scores, self.classes, self.index, self.counts)
 
 
@@ -123,8 +148,9 @@ _default = PostProcessor()
 
 def detect(preds_levels, img_size: int, conf: float = 0.4, iou: float = 0.5, max_det: int = 300,
            cap: Optional[int] = None) -> List[Dict[str, torch.Tensor]]:
-    """tools/infer.py:460-493 for a whole batch; defaults are the CLI's (conf 0.4, iou 0.5, 300 per class)."""
-    return _default(preds_levels, img_size, conf, iou, max_det, cap).to_list()
+    """tools/infer.py:460-493 for a whole batch; defaults are the CLI's (conf 0.4, iou 0.5, 300 per class).  Returns fresh
+    tensors (the shared PostProcessor's buffers are copied out)."""
+    return _default(preds_levels, img_size, conf, iou, max_det, cap).to_list(copy=True)
 
 
 def decode_batch_to_coco_dets(preds, img_size, conf_th=0.001, iou_th=0.65, add_one=True) -> List[List[dict]]:
