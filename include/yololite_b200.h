@@ -46,7 +46,8 @@ enum yl_op_kind {
   YL_OP_STEM2 = 4  /* fused conv_stem (3x3 s2, Cin=3, NCHW input, 32 ch, +bias+ReLU) -> dense 3x3 s2 conv + bias + act
                       (timm blocks.0.0): the stem activation (13 MB/image at 640 px) never leaves shared memory.
                       cin = 3, cout = channels of the second conv, k/stride/act = the second conv's, k2 = stem
-                      channels (32), w2_off = [27][32] stem weights followed by 32 stem biases, wt_off required  */
+                      channels (32), w2_off = [27][32] stem weights followed by 32 stem biases, wt_off required.
+                      Shapes the fused kernel cannot take (W % 4 != 0, cout > 32) run unfused: SIMT stem -> conv -> pointwise  */
 };
 enum yl_act { YL_ACT_NONE = 0, YL_ACT_RELU = 1, YL_ACT_SILU = 2 };
 
@@ -69,8 +70,8 @@ typedef struct yl_op {
   int64_t w_off;     /* float offset of the GEMM/stencil weights in the blob */
   int64_t b_off;     /* float offset of the bias (cout floats), or -1 */
   int64_t w2_off;    /* YL_OP_DWPW: float offset of depthwise weights [k2*k2][cin]; otherwise -1 */
-  int64_t wt_off;    /* float offset of the tcgen05 weight image [2 (hi,lo)][ceil(K/32)][ceil16(cout)][32], pre-split
-                        into TF32 hi/lo and pre-swizzled (SWIZZLE_128B, K-major), or -1 */
+  int64_t wt_off;    /* float offset of the tcgen05 weight image [ceil(K/32)][3 splits][ceil16(cout)][32 k] in bf16 (two per float
+                        slot): w = w1 + w2 + w3 pre-split and pre-swizzled (64 B rows, SWIZZLE_64B, K-major), or -1 */
   int64_t w3_off;    /* YL_OP_STEM2: float offset of the bf16-triple weight image of the fused stem kernel
                         ([9 taps][3 splits][ceil16(cout)][32] conv2 | [3 splits][32][32] stem incl. bias row k = 27, each
                         row 64 B, SWIZZLE_64B K-major, two bf16 per float slot; followed by a second [3 splits][32][32] stem image
@@ -90,7 +91,7 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
                      int32_t n_buffers, int32_t n_levels, int32_t device, yl_engine** out);
 int yl_engine_destroy(yl_engine* e);
 
-/* Engine options.  "tensor_cores": 1 (default) = run eligible convs on the tcgen05 3xTF32 kernel, 0 = fp32 SIMT kernels only.
+/* Engine options.  "tensor_cores": 1 (default) = run eligible convs on the tcgen05 bf16-triple kernel, 0 = fp32 SIMT kernels only.
  * "pdl": 1 (default) = launch the tcgen05 kernels with programmatic dependent launch (prologue overlaps the previous kernel's
  * tail).  "graph": 1 = capture each distinct call (same pointers, shape and thresholds) once into a CUDA graph and replay it
  * (default 0; the first call with new pointers runs eagerly, the second captures).  Unknown keys return an error.          */

@@ -49,7 +49,7 @@ def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0, stride2=0):
         wsm = g.randn(27, 32) / 5
         bsv = g.randn(32) * 0.3
         op.w3_off = add(packer.stem2_image(wm, cout, wsm, bsv))
-        op.w2_off = add(np.concatenate([wsm.reshape(-1), bsv, packer.tc_image(np.concatenate([wsm, bsv.reshape(1, -1)]), 32).astype(np.float64)]))
+        op.w2_off = add(np.concatenate([wsm.reshape(-1), bsv]))
     else:
         kk = 1 if kind == "dwpw" else k
         wm = np.zeros((kk * kk * cin, (cout + 3) // 4 * 4))

@@ -35,8 +35,11 @@ def test_detect_one_call_equals_forward_plus_postprocess_and_graph_replay():
     for graph in (False, True):
         eng = _engine(ck, graph=graph)
         cap0 = _stat("graph_captures")
-        for rep in range(4):           # graph mode: 1st call eager, 2nd captures, later ones replay
-            bx, sc, cl, ix, cn = eng.detect(x, 320, 0.25, 0.5, 300, cap=512)
+        bufs = (torch.empty((3, 512, 4), device="cuda"), torch.empty((3, 512), device="cuda"),
+                torch.empty((3, 512), device="cuda", dtype=torch.int64), torch.empty((3, 512), device="cuda", dtype=torch.int64),
+                torch.zeros((3,), device="cuda", dtype=torch.int32))
+        for rep in range(4):           # graph mode: 1st call eager, 2nd captures, later ones replay (same pointers every call)
+            bx, sc, cl, ix, cn = eng.detect(x, 320, 0.25, 0.5, 300, cap=512, outputs=bufs)
             got = y.Detections(bx, sc, cl, ix, cn).to_list()
             for g, w in zip(got, wl):
                 assert torch.equal(g["index"], w["index"]) and torch.equal(g["boxes"], w["boxes"])
@@ -101,7 +104,7 @@ def test_packed_payload_written_by_the_kernel():
     lv = [torch.from_numpy((rng.randn(3, 1, s, s, 9) * 2).astype(np.float32)).cuda() for s in (16, 8, 4)]
     for l in lv:
         l[..., 4] += 1.0
-    cap = 64
+    cap = 336                                            # = N: cannot overflow
     pp = y.PostProcessor()
     packed = torch.full((3, cap + 1, 6), -7.0, device="cuda")
     d = pp(lv, 128, 0.25, 0.5, 300, cap=cap, packed=packed)

@@ -1,4 +1,4 @@
-"""Single-kernel numerics through yl_run_op: every conv kernel (fp32 SIMT and tcgen05 3xTF32) against a plain
+"""Single-kernel numerics through yl_run_op: every conv kernel (fp32 SIMT and tcgen05 bf16-triple) against a plain
 PyTorch fp32 (CPU) convolution of the same op.  Tolerance 2e-4 abs on O(1) activations (fp32 accumulation-order
 noise is ~1e-6; a single-pass TF32 product would show ~1e-2 here)."""
 import ctypes
@@ -231,7 +231,8 @@ def test_tensor_core_path_is_not_single_pass_tf32():
 @pytest.mark.parametrize("hw,n2", [((64, 64), 16), ((45, 52), 16), ((83, 38), 32), ((640, 640), 16), ((96, 100), 12), ((33, 36), 16)])
 def test_fused_stem_conv(hw, n2, bf16x3, pw):
     """YL_OP_STEM2: conv_stem (3x3 s2, 3->32, ReLU) -> 3x3 s2 conv (32->n2, ReLU) in one tcgen05 kernel.
-    bf16x3 = the bf16-triple kernel (csrc/stem_kernel.cu, w3_off image); otherwise the older 3xTF32 kernel (w3_off = -1)."""
+    bf16x3 = the fused bf16-triple kernel (csrc/stem_kernel.cu, w3_off image); otherwise (w3_off = -1, or a shape the fused kernel
+    cannot take: W % 4 != 0, n2 % 4 != 0) the unfused fallback: SIMT stem -> 3x3 s2 conv -> pointwise as separate launches."""
     from yololite_b200 import _lib as L, packer
     if pw and n2 != 16:
         pytest.skip("the fused pointwise conv is the 16-channel blocks.0.1 of mobilenetv4_conv_small_050")
@@ -261,7 +262,7 @@ def test_fused_stem_conv(hw, n2, bf16x3, pw):
     op.w_off = add(wm)
     op.wt_off = add(packer.tc_image(wm, n2))
     wsm = np.transpose(ws.double().numpy(), (2, 3, 1, 0)).reshape(27, 32)
-    op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy(), packer.tc_image(np.concatenate([wsm, bs.double().numpy().reshape(1, -1)]), 32).astype(np.float64)]))
+    op.w2_off = add(np.concatenate([wsm.reshape(-1), bs.double().numpy()]))
     op.w3_off = add(packer.stem2_image(wm, n2, wsm, bs.double().numpy())) if bf16x3 else -1
     op.b_off = add(packer._pad4(b2.double().numpy()))
     want = F.relu(F.conv2d(F.relu(F.conv2d(x, ws, bs, stride=2, padding=1)), w2, b2, stride=2, padding=1))

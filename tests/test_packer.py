@@ -87,24 +87,27 @@ def test_product_synth_checkpoint_matches_reference_state_dict_spec():
 
 
 def test_tc_weight_image_layout():
-    """[2][nslab][Npad][32] with hi/lo split and the SWIZZLE_128B chunk permutation, checked element by element."""
+    """[nslab][3 splits][Npad][32 k] bf16 with the SWIZZLE_64B chunk permutation, checked element by element; the three splits
+    reproduce the fp32 weight to 2^-24."""
     rng = np.random.RandomState(0)
+
+    def bf(u16):
+        return (np.uint32(u16) << np.uint32(16)).view(np.float32) if isinstance(u16, np.ndarray) else np.array([u16], np.uint32).__lshift__(16).view(np.float32)[0]
     for K, N in ((27, 32), (48, 85), (96, 96), (288, 16)):
         wm = rng.randn(K, (N + 3) // 4 * 4)
-        img = packer.tc_image(wm, N)
+        img = packer.tc_image(wm, N).view(np.uint16)
         nslab, npad = (K + 31) // 32, (N + 15) // 16 * 16
-        assert img.size == 2 * nslab * npad * 32
-        w32 = wm.astype(np.float32)
+        assert img.size == nslab * 3 * npad * 32
+        img = img.reshape(nslab, 3, npad, 32)
         for _ in range(300):
             k, n = int(rng.randint(0, nslab * 32)), int(rng.randint(0, npad))
             s, kk = divmod(k, 32)
-            pos = (((kk // 4) ^ (n % 8)) * 4) + kk % 4
-            want = w32[k, n] if (k < K and n < N) else np.float32(0)
-            hi = packer.tf32_rn(np.array([want], np.float32))[0]
-            lo = packer.tf32_rn(np.array([want - hi], np.float32))[0]
-            assert img[((0 * nslab + s) * npad + n) * 32 + pos] == hi
-            assert img[((1 * nslab + s) * npad + n) * 32 + pos] == lo
-            assert abs(float(want) - float(hi) - float(lo)) <= abs(float(want)) * 2.0 ** -21
+            pos = (((kk // 8) ^ ((n >> 1) & 3)) * 8) + kk % 8
+            want = wm[k, n] if (k < K and n < N) else 0.0
+            parts = [float(bf(img[s, q, n, pos])) for q in range(3)]
+            assert abs(want - sum(parts)) <= abs(want) * 2.0 ** -23 + 1e-30
+            if want:
+                assert abs(parts[0] - want) <= abs(want) * 2.0 ** -8 and abs(parts[1]) <= abs(want) * 2.0 ** -8
 
 
 def test_stem_u8_matrix_reproduces_normalise_then_conv():

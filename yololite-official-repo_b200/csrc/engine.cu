@@ -89,7 +89,7 @@ struct yl_engine {
   std::vector<int> level_shape;  // n_levels * 4
   std::vector<size_t> level_off; // engine-owned level buffers (yl_engine_detect) inside the arena
   std::vector<int> op_hout, op_wout, op_hin, op_win, op_hu, op_wu;
-  size_t stem_tmp_off = 0;       // unfused stem fallback: intermediate [B,Ho,Wo,C] buffer (only when the fused kernel cannot run)
+  size_t stem_tmp_off = 0, stem_mid_off = 0;   // unfused stem fallback: stem activation / conv2 output (only when the fused kernel cannot run)
   bool has_stem_tmp = false;
   size_t post_scratch_off = 0, post_scratch_bytes = 0;
   long long n_anchors = 0;
@@ -170,20 +170,35 @@ static int launch_simt(const yl_op& op, const ConvParams& p, cudaStream_t st) {
 
 static const int g_old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
 
-// YL_OP_STEM2 when the fused bf16 kernel cannot take the shape (W % 4 != 0, more than 32 conv2 channels ...): the older tf32
-// kernel for conv_stem -> conv2, then the fused pointwise conv (timm blocks.0.1) as a separate SIMT launch through `tmp`.
-static int run_stem2_unfused(const yl_op& op, const ConvParams& p, const float* blob, float* tmp, int sm_count, cudaStream_t st) {
+// YL_OP_STEM2 when the fused bf16 kernel cannot take the shape (W % 4 != 0, more than 32 conv2 channels ...): conv_stem on the
+// fp32 SIMT kernel into `tmp_stem` [B,Hs,Ws,32], the 3x3 s2 conv as an ordinary dense conv, then the fused pointwise conv (timm
+// blocks.0.1) as its own launch through `tmp_mid` [B,Ho,Wo,cout].
+static int run_stem2_unfused(const yl_op& op, const ConvParams& p, const float* blob, float* tmp_stem, float* tmp_mid, int use_tc,
+                             int sm_count, cudaStream_t st) {
   YL_REQUIRE(!p.in_u8, "uint8 image input needs the fused bf16 stem kernel (16/32-channel second conv, even H, W % 16 == 0)");
-  ConvParams q = p;
-  if (p.b2) {
-    YL_REQUIRE(tmp != nullptr, "unfused stem fallback needs the intermediate buffer (plan the engine for this shape first)");
-    q.out = tmp; q.b2 = nullptr; q.act2 = YL_ACT_NONE;
+  YL_REQUIRE(tmp_stem && (!p.b2 || tmp_mid), "unfused stem fallback needs its intermediate buffers (plan the engine for this shape first)");
+  const int sc = op.k2;                                           // stem channels
+  const int Hs = (p.Hin + 2 - 3) / 2 + 1, Ws = (p.Win + 2 - 3) / 2 + 1;
+  ConvParams s{};
+  s.in = p.in; s.w = blob + op.w2_off; s.bias = s.w + 27 * sc; s.out = tmp_stem;
+  s.B = p.B; s.Hin = p.Hin; s.Win = p.Win; s.Cin = 3; s.Hout = Hs; s.Wout = Ws; s.Cout = sc;
+  s.KS = 3; s.stride = 2; s.pad = 1; s.act = YL_ACT_RELU;
+  ++g_simt_launches;
+  if (int rc = launch_stem(s, st)) return rc;
+  ConvParams c2{};
+  c2.in = tmp_stem; c2.w = p.w; c2.bias = p.bias; c2.out = p.b2 ? tmp_mid : p.out;
+  c2.B = p.B; c2.Hin = Hs; c2.Win = Ws; c2.Cin = sc; c2.Hout = p.Hout; c2.Wout = p.Wout; c2.Cout = op.cout;
+  c2.KS = op.k; c2.stride = op.stride; c2.pad = op.k / 2; c2.act = p.act;
+  if (use_tc && op.wt_off >= 0 && op.cout >= 32 && (op.cout & 3) == 0 && tc_supported(op.k * op.k * sc, op.cout, 0, 1, 0, p.Hout, p.Wout, 1)) {
+    ++g_tc_launches;
+    if (int rc = launch_tc_conv(c2, blob + op.wt_off, 1, sm_count, st)) return rc;
+  } else {
+    ++g_simt_launches;
+    if (int rc = launch_conv_gemm(c2, st)) return rc;
   }
-  ++g_tc_launches;
-  if (int rc = launch_tc_conv(q, blob + op.wt_off, 3, sm_count, st)) return rc;
   if (p.b2) {
     ConvParams r{};
-    r.in = tmp; r.w = p.b2; r.bias = p.b2 + (size_t)op.cout * op.cout; r.out = p.out;
+    r.in = tmp_mid; r.w = p.b2; r.bias = p.b2 + (size_t)op.cout * op.cout; r.out = p.out;
     r.B = p.B; r.Hin = p.Hout; r.Win = p.Wout; r.Cin = op.cout; r.Hout = p.Hout; r.Wout = p.Wout; r.Cout = op.cout;
     r.KS = 1; r.stride = 1; r.pad = 0; r.act = p.act2;
     ++g_simt_launches;
@@ -195,7 +210,7 @@ static int run_stem2_unfused(const yl_op& op, const ConvParams& p, const float* 
 // One op, no caching (yl_run_op and the profile path).
 static int run_op(const yl_op& op, const float* blob, const float* in, const float* res, const float* up, float* out, int B,
                   int hin, int win, int hout, int wout, int hu, int wu, int use_tc, int sm_count, cudaStream_t st,
-                  const unsigned char* in_u8 = nullptr, float* stem_tmp = nullptr) {
+                  const unsigned char* in_u8 = nullptr) {
   ConvParams p;
   fill_params(p, op, blob, in, res, up, out, B, hin, win, hout, wout, hu, wu, in_u8);
   if (op.kind == YL_OP_STEM2) {
@@ -205,7 +220,15 @@ static int run_op(const yl_op& op, const float* blob, const float* in, const flo
       if (int rc = stem2_prepare(p, blob + op.w3_off, sm_count, &L)) return rc;
       return stem2_launch(L, st, 0);
     }
-    return run_stem2_unfused(op, p, blob, stem_tmp, sm_count, st);
+    // single-op API: stream-ordered temporaries
+    const size_t hs = (hin + 2 - 3) / 2 + 1, ws = (win + 2 - 3) / 2 + 1;
+    float *t1 = nullptr, *t2 = nullptr;
+    YL_CHECK_CUDA(cudaMallocAsync(&t1, (size_t)B * hs * ws * op.k2 * sizeof(float), st));
+    if (op.b2_off >= 0) YL_CHECK_CUDA(cudaMallocAsync(&t2, (size_t)B * hout * wout * op.cout * sizeof(float), st));
+    const int rc = run_stem2_unfused(op, p, blob, t1, t2, use_tc, sm_count, st);
+    cudaFreeAsync(t1, st);
+    if (t2) cudaFreeAsync(t2, st);
+    return rc;
   }
   const int mode = tc_mode_for(op, p, use_tc, hout, wout);
   if (mode >= 0) { ++g_tc_launches; return launch_tc_conv(p, blob + op.wt_off, mode, sm_count, st); }
@@ -231,7 +254,7 @@ static int plan(yl_engine* e, int B, int H, int W, const int32_t* feat_dims) {
   std::vector<int> lvl(e->n_levels * 4, 0);
   e->op_hout.assign(nops, 0); e->op_wout.assign(nops, 0); e->op_hin.assign(nops, 0); e->op_win.assign(nops, 0);
   e->op_hu.assign(nops, 0); e->op_wu.assign(nops, 0);
-  size_t stem_tmp_bytes = 0;
+  size_t stem_tmp_bytes = 0, stem_mid_bytes = 0;
   for (int i = 0; i < nops; ++i) {
     const yl_op& op = e->ops[i];
     int hin, win, cin;
@@ -265,7 +288,10 @@ static int plan(yl_engine* e, int B, int H, int W, const int32_t* feat_dims) {
       // the fused kernel needs W % 4 == 0 (TMA row pitch) and <= 32 conv2 channels; otherwise the unfused fallback runs and a
       // fused pointwise conv needs an intermediate tensor
       const bool fused_ok = op.w3_off >= 0 && !g_old_stem && (W & 3) == 0 && op.cout <= 32 && (op.cout & 3) == 0;
-      if (!fused_ok && op.b2_off >= 0) stem_tmp_bytes = std::max(stem_tmp_bytes, (size_t)B * hout * wout * op.cout * sizeof(float));
+      if (!fused_ok) {
+        stem_tmp_bytes = std::max(stem_tmp_bytes, (size_t)B * ((H + 2 - 3) / 2 + 1) * ((W + 2 - 3) / 2 + 1) * op.k2 * sizeof(float));
+        if (op.b2_off >= 0) stem_mid_bytes = std::max(stem_mid_bytes, (size_t)B * hout * wout * op.cout * sizeof(float));
+      }
     }
     e->op_hin[i] = hin; e->op_win[i] = win; e->op_hout[i] = hout; e->op_wout[i] = wout;
     if (op.dst >= 0) {
@@ -291,6 +317,7 @@ static int plan(yl_engine* e, int B, int H, int W, const int32_t* feat_dims) {
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
   for (auto& b : bufs) b.off = take(b.bytes);
   e->stem_tmp_off = take(stem_tmp_bytes);
+  e->stem_mid_off = take(stem_mid_bytes);
   e->has_stem_tmp = stem_tmp_bytes > 0;
   // engine-owned output levels + postprocess scratch (yl_engine_detect)
   std::vector<size_t> loff(e->n_levels);
@@ -334,7 +361,8 @@ static int launch_cached(yl_engine* e, int i, const float* in, const unsigned ch
   rec.in = in; rec.in_u8 = in_u8; rec.out = out; rec.res = res; rec.up = up;
   if (op.kind == YL_OP_STEM2) {
     if (!(op.w3_off >= 0 && !g_old_stem && stem2_supported(p)))
-      return run_stem2_unfused(op, p, e->d_blob, e->has_stem_tmp ? reinterpret_cast<float*>(e->arena + e->stem_tmp_off) : nullptr, e->sm_count, st);
+      return run_stem2_unfused(op, p, e->d_blob, e->has_stem_tmp ? reinterpret_cast<float*>(e->arena + e->stem_tmp_off) : nullptr,
+                               e->has_stem_tmp ? reinterpret_cast<float*>(e->arena + e->stem_mid_off) : nullptr, e->use_tc, e->sm_count, st);
     rec.kind = 2;
     if (int rc = stem2_prepare(p, e->d_blob + op.w3_off, e->sm_count, &rec.s2)) return rc;
   } else {

@@ -49,11 +49,10 @@ inline int once_per_device(bool* done /*[64]*/, std::mutex& m, F set) {
 
 struct TcParams {
   ConvParams c;
-  const float* wimg;   // [2 (hi,lo)][nslab][Npad][32] pre-swizzled
-  int mode;            // 0 pointwise, 1 im2col (Cin%4==0), 2 depthwise KSxKS -> pointwise, 3 stem -> 3x3 s2 (older tf32 kernel)
+  const float* wimg;   // bf16-triple image [nslab][3 splits][Npad][32 k], 64 B rows pre-swizzled (SWIZZLE_64B), see packer.tc_image
+  int mode;            // 0 pointwise, 1 dense KxK as im2col (Cin%4==0), 2 depthwise KSxKS -> pointwise
   int K, nslab, Npad, Nc, nchunks, stages, tmem_cols;
-  int Hs, Ws;           // MODE 3: stem output size
-  int tiles_x, tiles_y; // MODE 2/3: spatial tiles (8 rows x 16 cols of output pixels) per image
+  int tiles_x, tiles_y; // spatial modes: tiles per image
   int halo_slots;       // MODE 2: halo ring depth
   int tile_w, tile_h;   // MODE 2: spatial tile of output pixels (tile_w % 4 == 0, tile_w * tile_h <= 128)
   int dw_stride;        // MODE 2: stride of the depthwise stage (1 or 2); the output tile is tile_w x tile_h, the halo covers
@@ -68,7 +67,6 @@ struct TcParams {
   int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
                         // streamed from L2 into the A stage's own W slot with cp.async.bulk
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
-  int raw_hi;          // 1: the tensor core reads the raw fp32 A (it drops the low 13 mantissa bits itself); only lo is written
   long long M;
   int num_tiles;
 };

@@ -1,24 +1,29 @@
-// tcgen05 implicit-GEMM convolution with error-compensated 3xTF32 operands (sm_100a).
+// tcgen05 implicit-GEMM convolution with error-compensated bf16-triple operands (sm_100a).
 //
 //   C[M, N] = A[M, K] * W[K, N]      M = B*Hout*Wout pixels, K = taps*Cin, N = Cout
 //
-// Why 3xTF32: the parity bar is 1e-3 abs on logits after a 69-conv stack; single-pass TF32/BF16/FP16 operands
-// miss it by two orders of magnitude, fp32 SIMT FMA is ~5x below the HBM roofline
-// for the 96-channel pointwise layers.  Every fp32 operand x is split exactly into hi = x & 0xFFFFE000 (a TF32
-// value) and lo = x - hi; D = Ahi*Whi + Alo*Whi + Ahi*Wlo accumulates in fp32 in TMEM (dropped term ~2^-22).
+// Why error compensation: the parity bar is 1e-3 abs on logits after a 69-conv stack; single-pass TF32/BF16/FP16 operands
+// miss it by two orders of magnitude, fp32 SIMT FMA is ~5x below the HBM roofline for the
+// 96-channel pointwise layers.  Why bf16 triples and not 3xTF32: the tensor core does not round its fp32 accumulator, it
+// truncates (the addends are aligned to the largest exponent and cut), which biases every instruction toward zero by ~1.5 ulp
+// when the products carry 22 significant bits (TF32 x TF32) -- measured -3.7 / -7.8 / -26 ulp per layer at K = 96 / 256 / 960
+// (experiments/exp_accum.cu), and the bias adds up LINEARLY over the layers (1.5e-3 on edge_m's logits).  With x = x1 + x2 + x3
+// (bf16 each) the large-magnitude chain A1*W1 has 16-bit products that mostly fit the accumulator exactly and takes half as
+// many instructions (K = 16): -0.5 / -1.4 / -6 ulp.  D = A1*W1 (main accumulator) + A1*W2 + A2*W1 + A2*W2 + A1*W3 + A3*W1
+// (correction accumulator, 2^-8 smaller; dropped terms 2^-24), five instructions per 16-wide k-step -- the first one,
+// A1 x [W1|W2], fills both accumulators at once -- at the same tensor-pipe time as 3xTF32 and 25 % less shared memory.
 //
-// Structure (one persistent CTA per SM, 13 warps, warp-specialised):
-//   warps 0-7  producers: read the A tile from HBM with coalesced 16 B loads (or compute it: depthwise 3x3 for the
-//              fused DWConvBlock, im2col gather for dense 3x3, NCHW gather for the stem), split hi/lo in registers,
-//              st.shared into the canonical K-major SWIZZLE_128B UMMA layout (32 fp32 = one 128 B row per K-slab),
+// Structure (one persistent CTA per SM, 14 warps, warp-specialised):
+//   warps 0-7  producers: bring the fp32 A tile in (TMA / cp.async, or compute it: depthwise KxK for the fused DWConvBlock,
+//              im2col gather for dense 3x3), split it into three bf16 planes in the K-major UMMA layouts
+//              (stage = [a1 | a2] as one 128 B SWIZZLE_128B row per pixel and K-slab + a3 as a 64 B SWIZZLE_64B row),
 //              fence.proxy.async, arrive on the stage's "full" mbarrier;
-//   warp  12   one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=Nc, K=8 per instruction,
-//              3 passes per k-step) into one of two TMEM accumulators, tcgen05.commit frees the smem stage /
-//              publishes the accumulator;
-//   warps 8-11 epilogue: tcgen05.ld 32 lanes x 16 columns, + bias (folded BN) + residual + nearest-upsampled
-//              coarser level + ReLU/SiLU, 16 B stores (head layout [B,A,S,S,5+C] written directly).
-// The weight image (hi and lo, pre-split and pre-swizzled on the host) stays resident in shared memory for the
-// CTA's lifetime.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
+//   warp  12   one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (bf16, M=128, K=16 per instruction) into one of
+//              two TMEM accumulator pairs, tcgen05.commit frees the smem stage / publishes the accumulators;
+//   warps 8-11 epilogue: tcgen05.ld, main + corr, + bias (folded BN) + residual + nearest-upsampled coarser level +
+//              ReLU/SiLU, TMA tensor stores / 16 B stores (head layout [B,A,S,S,5+C] written directly).
+// The weight image (three bf16 splits, pre-swizzled on the host) stays resident in shared memory for the CTA's lifetime or
+// is streamed per K-slab.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -38,16 +43,12 @@ constexpr int TC_TMA_WARP = 13;                  // MODE 2: one thread issues th
 constexpr int TC_THREADS = 32 * 14;
 constexpr int TC_MAX_HALO_SLOTS = 4;
 constexpr int TC_BM = 128;
-constexpr int TC_SLAB_BYTES = TC_BM * 128;      // one K-slab (32 fp32) of the A tile
+constexpr int TC_P12_BYTES = TC_BM * 128;       // planes a1 | a2 of one K-slab: 128 B per row (32 bf16 + 32 bf16), SWIZZLE_128B
+constexpr int TC_P3_BYTES = TC_BM * 64;         // plane a3: 64 B per row, SWIZZLE_64B
+constexpr int TC_STAGE_BYTES = TC_P12_BYTES + TC_P3_BYTES;      // 24 KB per A stage
 constexpr int TC_SMEM_BUDGET = 226 * 1024;      // of the 227 KB a CTA may use
 constexpr int TC_MAX_STAGES = 4;
-constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // MODE 3 spatial tile = 128 output pixels (MODE 2 picks its own, see tc_plan)
-// MODE 3 (stem 3x3 s2 on the NCHW input -> 3x3 s2 conv): per 8x16 output tile the stem output halo is 17x33 pixels x 32 ch,
-// computed from a 3 x 35 x 67 input patch
-constexpr int S3_HALO_H = 2 * TC_TILE_H + 1, S3_HALO_W = 2 * TC_TILE_W + 1, S3_HALO_PIX = S3_HALO_H * S3_HALO_W;
-constexpr int S3_PATCH_H = 2 * S3_HALO_H + 1, S3_PATCH_W = 2 * S3_HALO_W + 1, S3_PATCH_PITCH = 68;
-constexpr int S3_PATCH_BYTES = 3 * S3_PATCH_H * S3_PATCH_PITCH * 4;      // 28560
-constexpr int S3_HALO_BYTES = S3_HALO_PIX * 128;                        // 71808
+constexpr int TC_TILE_H = 8, TC_TILE_W = 16;          // spatial tile of the dense KxK TMA path = 128 output pixels
 constexpr int TC_EPI_PITCH = 36;                      // floats per staged row: 16 B aligned, conflict-free for 128-bit access
 constexpr int TC_STG_BYTES = 5120;                    // per epilogue warp: the padded transpose tile (32 x 36 floats) or the 4 KB
                                                       // SWIZZLE_128B tile a TMA store reads; 1024 B aligned
@@ -81,12 +82,16 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   // version[46,48)=1 layout[61,64)=2)
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+__device__ __forceinline__ uint64_t make_desc64(uint32_t saddr) {
+  // K-major, SWIZZLE_64B (64 B rows), 8-row groups 512 B apart
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
 
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
@@ -106,9 +111,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// round-to-nearest onto the TF32 grid (10 explicit mantissa bits): unbiased, and exact for the tensor core
-__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -121,13 +123,28 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void split_store(unsigned char* hi_base, unsigned char* lo_base, int row, int chunk, float4 a) {
-  const uint32_t off = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);
-  float4 h, l;
-  h.x = tf32_rn(a.x); h.y = tf32_rn(a.y); h.z = tf32_rn(a.z); h.w = tf32_rn(a.w);
-  l.x = tf32_rn(a.x - h.x); l.y = tf32_rn(a.y - h.y); l.z = tf32_rn(a.z - h.z); l.w = tf32_rn(a.w - h.w);
-  *reinterpret_cast<float4*>(hi_base + off) = h;
-  *reinterpret_cast<float4*>(lo_base + off) = l;
+// two fp32 -> packed bf16 pair (element 0 in the low half) for each of the three splits: x = x1 + x2 + x3 up to 2^-24 |x|
+__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
+  a -= __uint_as_float(p1 << 16);
+  b -= __uint_as_float(p1 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
+  a -= __uint_as_float(p2 << 16);
+  b -= __uint_as_float(p2 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
+}
+
+// Write the three bf16 splits of 4 consecutive k (16 B fp32 source chunk `c` = k 4c..4c+3 of the K-slab) of A row `row` into a stage:
+//   a1 -> bytes [0,64) of the row's 128 B SWIZZLE_128B line, a2 -> bytes [64,128), a3 -> the row's 64 B SWIZZLE_64B line of the P3 plane.
+__device__ __forceinline__ void store_split3(unsigned char* stage, int row, int c, float4 a) {
+  uint2 s1, s2, s3;
+  split3(a.x, a.y, s1.x, s2.x, s3.x);
+  split3(a.z, a.w, s1.y, s2.y, s3.y);
+  const uint32_t r7 = (uint32_t)row & 7u, half = ((uint32_t)c & 1u) << 3, c2 = (uint32_t)c >> 1;
+  unsigned char* line = stage + (uint32_t)(row >> 3) * 1024u + r7 * 128u;
+  *reinterpret_cast<uint2*>(line + ((c2 ^ r7) << 4) + half) = s1;
+  *reinterpret_cast<uint2*>(line + (((4u + c2) ^ r7) << 4) + half) = s2;
+  *reinterpret_cast<uint2*>(stage + TC_P12_BYTES + (uint32_t)row * 64u + ((c2 ^ (((uint32_t)row >> 1) & 3u)) << 4) + half) = s3;
 }
 
 // SiLU / ReLU through one out-of-line helper keeps the (I-cache sensitive) epilogue small.
@@ -138,36 +155,6 @@ __device__ __noinline__ float4 act4(float4 o, int act) {
     o.x = silu_accurate(o.x); o.y = silu_accurate(o.y); o.z = silu_accurate(o.z); o.w = silu_accurate(o.w);
   }
   return o;
-}
-
-// One 16 B element of the A tile for output row (b, oy, ox) [already offset by stride/pad in (iy0, ix0)] at k.
-template <int MODE>
-__device__ __forceinline__ float4 load_a(const ConvParams& c, const float* rbase, int iy0, int ix0, int k, int tap_y, int tap_x,
-                                         int ci) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (MODE == 0) {
-    a = __ldg(reinterpret_cast<const float4*>(rbase + k));
-  } else if (MODE == 1) {
-    const int iy = iy0 + tap_y, ix = ix0 + tap_x;
-    if (iy >= 0 && iy < c.Hin && ix >= 0 && ix < c.Win)
-      a = __ldg(reinterpret_cast<const float4*>(rbase + ((size_t)iy * c.Win + ix) * c.Cin + ci));
-  } else {   // depthwise 3x3 (pad 1, stride 1) computed on the fly
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = iy0 + ky;
-      if (iy < 0 || iy >= c.Hin) continue;
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int ix = ix0 + kx;
-        if (ix < 0 || ix >= c.Win) continue;
-        const float4 x4 = __ldg(reinterpret_cast<const float4*>(rbase + ((size_t)iy * c.Win + ix) * c.Cin + k));
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(c.w2 + (ky * 3 + kx) * c.Cin + k));
-        a.x = fmaf(x4.x, w4.x, a.x); a.y = fmaf(x4.y, w4.y, a.y);
-        a.z = fmaf(x4.z, w4.z, a.z); a.w = fmaf(x4.w, w4.w, a.w);
-      }
-    }
-  }
-  return a;
 }
 
 template <int MODE, int KS>
@@ -181,24 +168,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   pdl_launch_dependents();      // the next kernel's prologue may overlap this kernel (it waits for our completion before reading)
 
   // ---- shared memory carve-up (all slabs 1024 B aligned)
-  const uint32_t w_slab_bytes = (uint32_t)p.Nc * 128u;
-  // resident weights: [hi: nslab slabs][lo: nslab slabs]; streamed (MODE 2, p.wstream): stages x (hi slab, lo slab)
+  // weights of one K-slab: three bf16 splits x Nc rows x 64 B (SWIZZLE_64B, K-major): [W1 | W2 | W3], so that [W1|W2] is one
+  // B operand of N = 2*Nc.  Resident: nslab slabs; streamed (p.wstream): one slab per A stage.
+  const uint32_t w_split_bytes = (uint32_t)p.Nc * 64u, w_slab_bytes = 3u * w_split_bytes;
   const int w_slabs = p.wstream ? p.stages : p.nslab;
-  unsigned char* w_hi = smem;
-  unsigned char* w_lo = w_hi + (size_t)w_slabs * w_slab_bytes;
-  unsigned char* a_ring = w_lo + (size_t)w_slabs * w_slab_bytes;                 // stages x (hi 16K, lo 16K)
-  unsigned char* stage_base = a_ring + (size_t)p.stages * 2 * TC_SLAB_BYTES;     // epilogue staging, 1024 B aligned
+  unsigned char* w_base = smem;
+  unsigned char* a_ring = w_base + (size_t)w_slabs * w_slab_bytes;               // stages x (a1|a2 16K, a3 8K)
+  unsigned char* stage_base = a_ring + (size_t)p.stages * TC_STAGE_BYTES;        // epilogue staging, 1024 B aligned
   unsigned char* halo = stage_base + (size_t)(p.epi2 ? 8 : 4) * p.stg_stride;     // MODE 2: halo_slots x halo_bytes
-  // MODE 3: `halo` region = stem weight image (hi 4 KB, lo 4 KB) | stem-output halo (71808 B) | input patch (28560 B)
-  float* w2s = reinterpret_cast<float*>(halo + ((MODE == 2 || (MODE == 1 && p.tma_a)) ? (size_t)p.halo_slots * p.halo_bytes : MODE == 3 ? (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES : 0));
+  float* w2s = reinterpret_cast<float*>(halo + ((MODE == 2 || (MODE == 1 && p.tma_a)) ? (size_t)p.halo_slots * p.halo_bytes : 0));
   // MODE 2: depthwise taps [KS*KS][nslab*32] followed by the depthwise bias row
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(w2s) + (MODE == 2 ? (size_t)(KS * KS + 1) * p.nslab * 32 * 4 : 0));
   uint64_t* full_bar = bars;                       // [stages]   producers -> MMA        (count: producer warps)
   uint64_t* empty_bar = bars + TC_MAX_STAGES;      // [stages]   MMA commit -> producers (count 1)
   uint64_t* tfull_bar = bars + 2 * TC_MAX_STAGES;  // [2]        MMA commit -> epilogue  (count 1)
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]        epilogue -> MMA         (count 4)
-  uint64_t* halo_full = tempty_bar + 2;            // MODE 3: epilogue (4 warps) -> producers: stem halo written
-  uint64_t* halo_empty = tempty_bar + 3;           // MODE 3: producers (8 warps) -> epilogue: halo consumed
   uint64_t* wfull_bar = tempty_bar + 4;            // [stages]   MODE 2 streamed weights: cp.async.bulk complete_tx -> MMA
   uint64_t* hfull_bar = wfull_bar + TC_MAX_STAGES;   // [halo_slots] MODE 2: TMA complete_tx -> producers
   uint64_t* hempty_bar = hfull_bar + TC_MAX_HALO_SLOTS;   // [halo_slots] MODE 2: producers (8 warps) -> TMA thread
@@ -215,27 +199,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       mbar_init(smem_u32(&full_bar[s]), MODE == 2 ? 4 : p.prod_warps); mbar_init(smem_u32(&empty_bar[s]), 1); mbar_init(smem_u32(&wfull_bar[s]), 1);
     }
     for (int a = 0; a < 2; ++a) { mbar_init(smem_u32(&tfull_bar[a]), 1); mbar_init(smem_u32(&tempty_bar[a]), 4); }
-    mbar_init(smem_u32(halo_full), 4);
-    mbar_init(smem_u32(halo_empty), TC_PROD_WARPS);
     for (int s = 0; s < TC_MAX_HALO_SLOTS; ++s) { mbar_init(smem_u32(&hfull_bar[s]), 1); mbar_init(smem_u32(&hempty_bar[s]), MODE == 2 ? 4 : TC_PROD_WARPS); }
     mbar_init(smem_u32(wres_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    // resident weight image (hi then lo, every slab's rows [chunk_n0, chunk_n0 + Nc)): bulk copies straight from the
+    // resident weight image (per slab the three splits' rows [chunk_n0, chunk_n0 + Nc)): bulk copies straight from the
     // pre-swizzled image in L2, asynchronous -- only the MMA thread waits for them, before its first instruction
     if (!p.wstream) {
       const int rows = min(p.Nc, p.Npad - chunk_n0);              // rows of this chunk that exist in the image
       const uint32_t bar = smem_u32(wres_bar);
       if (p.nchunks == 1) {                                         // the whole image is one contiguous block
-        const uint32_t bytes = 2u * (uint32_t)p.nslab * w_slab_bytes;
+        const uint32_t bytes = (uint32_t)p.nslab * w_slab_bytes;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(w_hi)), "l"(p.wimg), "r"(bytes), "r"(bar) : "memory");
+                     ::"r"(smem_u32(w_base)), "l"(p.wimg), "r"(bytes), "r"(bar) : "memory");
       } else {
-        const uint32_t bytes = (uint32_t)rows * 128u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * (uint32_t)p.nslab * bytes) : "memory");
-        for (int ps = 0; ps < 2 * p.nslab; ++ps)
+        const uint32_t bytes = (uint32_t)rows * 64u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3u * (uint32_t)p.nslab * bytes) : "memory");
+        for (int ps = 0; ps < 3 * p.nslab; ++ps)
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                       ::"r"(smem_u32(w_hi) + (uint32_t)ps * w_slab_bytes), "l"(p.wimg + ((size_t)ps * p.Npad + chunk_n0) * 32), "r"(bytes), "r"(bar)
+                       ::"r"(smem_u32(w_base) + (uint32_t)ps * w_split_bytes), "l"(p.wimg + ((size_t)ps * p.Npad + chunk_n0) * 16), "r"(bytes), "r"(bar)
                        : "memory");
       }
     }
@@ -247,17 +229,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   }
   // rows of a partial last chunk that lie past the image are zero (generic stores; disjoint from the bulk copies)
   if (!p.wstream && chunk_n0 + p.Nc > p.Npad) {
-    const int rows = p.Npad - chunk_n0, zr = p.Nc - rows;          // zr zero rows at the end of every slab
-    for (int i = threadIdx.x; i < 2 * p.nslab * zr * 8; i += blockDim.x) {
-      const int ps = i / (zr * 8), r = i - ps * (zr * 8);
-      reinterpret_cast<float4*>(w_hi + (size_t)ps * w_slab_bytes + (size_t)rows * 128)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int rows = p.Npad - chunk_n0, zr = p.Nc - rows;          // zr zero rows at the end of every split block
+    for (int i = threadIdx.x; i < 3 * p.nslab * zr * 4; i += blockDim.x) {
+      const int ps = i / (zr * 4), r = i - ps * (zr * 4);
+      reinterpret_cast<float4*>(w_base + (size_t)ps * w_split_bytes + (size_t)rows * 64)[r] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_s[i] = (c.bias && i < p.Nc && chunk_n0 + i < c.Cout) ? __ldg(c.bias + chunk_n0 + i) : 0.f;
-  if (MODE == 3) {   // stem weight image [2][32 rows][32 k], pre-swizzled, right after the 27x32 weights + 32 biases
-    for (int i = threadIdx.x; i < 512; i += TC_THREADS)
-      reinterpret_cast<float4*>(halo)[i] = __ldg(reinterpret_cast<const float4*>(c.w2 + 896) + i);
-  }
   if (MODE == 2) {
     const int cp = p.nslab * 32;
     for (int i = threadIdx.x; i < (KS * KS + 1) * cp; i += TC_THREADS) {
@@ -282,125 +260,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
     const int ch = t & 7, r0 = t >> 3;
-    if (MODE == 3) {
-      // Fused stem: per 8x16 output tile, conv_stem (3x3 s2, Cin=3, NCHW input) is itself run on the tensor cores as five
-      // 128-row GEMM tiles over the 17x33 halo of its output (A = im2col of a 3x35x67 input patch held in shared memory,
-      // K = 27 padded to 32, N = 32); the epilogue warps write bias+ReLU of those into a shared-memory halo (exactly zero
-      // outside the stem output = the second conv's padding); the 9 taps of the second 3x3 s2 conv are then 9 K-slabs
-      // gathered from that halo.  The 13 MB/image stem activation never exists in HBM.
-      unsigned char* halb = halo + 8192;
-      float* patch = reinterpret_cast<float*>(halb + S3_HALO_BYTES);
-      const int per_img = p.tiles_x * p.tiles_y;
-      const size_t plane = (size_t)c.Hin * c.Win;
-      const int pw = t >> 5;                          // producer warp 0..7
-      // this thread's 4 k's of the stem im2col row: k = 4*ch + q = (ky*3 + kx)*3 + ci
-      int poff[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int k = ch * 4 + q, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-        poff[q] = k < 27 ? (ci * S3_PATCH_H + ky) * S3_PATCH_PITCH + kx : -1;
-      }
-      uint32_t soff[4];
-      int hp0[4];                                     // halo pixel of tap (0,0) for this thread's 4 output rows
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = r0 + 32 * i;
-        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-        hp0[i] = 2 * (row >> 4) * S3_HALO_W + 2 * (row & 15);
-      }
-      auto issue_patch = [&](int tile) {
-        if (tile < tiles) {
-          const int b = tile / per_img, rem = tile - b * per_img;
-          const int iy0 = (rem / p.tiles_x) * TC_TILE_H * 4 - 3, ix0 = (rem % p.tiles_x) * TC_TILE_W * 4 - 3;
-          const float* img = c.in + (size_t)b * 3 * plane;
-          for (int row = pw; row < 3 * S3_PATCH_H; row += TC_PROD_WARPS) {      // row = ci*35 + pr
-            const int ci = row / S3_PATCH_H, iy = iy0 + row - ci * S3_PATCH_H;
-            const bool rok = iy >= 0 && iy < c.Hin;
-            const float* srow = img + ci * plane + (size_t)(rok ? iy : 0) * c.Win;
-            const uint32_t drow = smem_u32(patch + row * S3_PATCH_PITCH);
-#pragma unroll
-            for (int u = 0; u < 3; ++u) {
-              const int pc = lane + 32 * u;
-              if (pc < S3_PATCH_W) {
-                const int ix = ix0 + pc;
-                const bool ok = rok && ix >= 0 && ix < c.Win;
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(drow + pc * 4), "l"(ok ? srow + ix : c.in),
-                             "r"(ok ? 4u : 0u) : "memory");
-              }
-            }
-          }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-      };
-      issue_patch(blockIdx.x);
-      int stage = 0;
-      uint32_t phase = 0, hphase = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        asm volatile("bar.sync 1, 256;" ::: "memory");              // patch landed for everyone
-        // ---- stem A tiles: 5 x 128 halo pixels, one K-slab each (k = 27 is the constant 1 that multiplies the bias row)
-        {
-          int hy = r0 / S3_HALO_W, hx = r0 - hy * S3_HALO_W;         // pixel r0 of the halo, then steps of 32 pixels
-          for (int j = 0; j < 5; ++j) {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const bool ok = hy < S3_HALO_H;
-              const float* pb = patch + 2 * hy * S3_PATCH_PITCH + 2 * hx;
-              float e[4];
-#pragma unroll
-              for (int q = 0; q < 4; ++q) e[q] = (ok && poff[q] >= 0) ? pb[poff[q]] : 0.f;
-              if (ch == 6) e[3] = ok ? 1.f : 0.f;
-              float4 l;
-              l.x = e[0] - __uint_as_float(__float_as_uint(e[0]) & 0xFFFFE000u);
-              l.y = e[1] - __uint_as_float(__float_as_uint(e[1]) & 0xFFFFE000u);
-              l.z = e[2] - __uint_as_float(__float_as_uint(e[2]) & 0xFFFFE000u);
-              l.w = e[3] - __uint_as_float(__float_as_uint(e[3]) & 0xFFFFE000u);
-              *reinterpret_cast<float4*>(hi + soff[i]) = make_float4(e[0], e[1], e[2], e[3]);
-              *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
-              hx += 32;
-              if (hx >= S3_HALO_W) { hx -= S3_HALO_W; ++hy; }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-          }
-        }
-        asm volatile("bar.sync 1, 256;" ::: "memory");              // everyone is done reading the patch
-        issue_patch(tile + gridDim.x);
-        mbar_wait(smem_u32(halo_full), hphase);                     // the epilogue warps have written this tile's halo
-        hphase ^= 1;
-        // ---- the 9 taps = 9 K-slabs gathered from the halo (chunk c of pixel q sits at position c ^ (q & 7))
-        for (int s = 0; s < 9; ++s) {
-          const int tapoff = (s / 3) * S3_HALO_W + (s % 3);
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int hp = hp0[i] + tapoff;
-            const float4 a = *reinterpret_cast<const float4*>(halb + hp * 128 + ((ch ^ (hp & 7)) << 4));
-            float4 l;
-            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(hi + soff[i]) = a;              // the tensor core drops the low 13 bits itself
-            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(halo_empty));           // this warp no longer reads the halo
-      }
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else if (MODE == 0 && p.tma_a) {
-      // The TMA warp lands each K-slab of the A tile (raw fp32 = the hi operand) straight in the swizzled UMMA layout;
-      // every producer thread derives lo = a - trunc_tf32(a) for its own 16 B pieces (4 with 8 producer warps, 8 with 4).
+    if (MODE == 0 && p.tma_a) {
+      // The TMA warp lands each K-slab of the fp32 A tile (128 rows x 128 B, SWIZZLE_128B) in the stage's a1|a2 area; every producer
+      // thread reads its own 16 B pieces (4 with 8 producer warps, 8 with 4), and -- a warp covers whole rows, so a __syncwarp
+      // separates all reads of a row from the writes -- overwrites the rows IN PLACE with the bf16 splits a1 | a2 (a3 goes to
+      // the stage's second plane).
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
       const int rstep = p.prod_warps * 4;                         // rows covered by one pass of the producer threads
@@ -409,31 +273,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       uint32_t phase = 0;
       for (int j = 0; j < total; ++j) {
         mbar_wait(smem_u32(&wfull_bar[stage]), phase);
-        unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+        unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
         for (int ps = 0; ps < npass; ++ps) {
-          uint32_t soff[4];
           float4 a[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int row = r0 + rstep * (4 * ps + i);
-            soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-            a[i] = *reinterpret_cast<const float4*>(hi + soff[i]);
+            a[i] = *reinterpret_cast<const float4*>(st + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4));
           }
+          __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 h, l;
-            if (p.raw_hi) {
-              l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
-              l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
-              l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
-              l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
-            } else {
-              h.x = tf32_rn(a[i].x); h.y = tf32_rn(a[i].y); h.z = tf32_rn(a[i].z); h.w = tf32_rn(a[i].w);
-              l.x = tf32_rn(a[i].x - h.x); l.y = tf32_rn(a[i].y - h.y); l.z = tf32_rn(a[i].z - h.z); l.w = tf32_rn(a[i].w - h.w);
-              *reinterpret_cast<float4*>(hi + soff[i]) = h;
-            }
-            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
-          }
+          for (int i = 0; i < 4; ++i) store_split3(st, r0 + rstep * (4 * ps + i), ch, a[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -443,16 +293,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     } else if (MODE == 1 && p.tma_a) {
       // Dense KxK conv with a small Cin (timm blocks.1.0: 3x3 s2, 16 -> 48): the whole-Cin halo of the INPUT for one spatial
       // tile of 8 x 16 output pixels arrives as ONE TMA box; the im2col K-slabs are gathered shared -> shared (a 16 B piece
-      // never straddles a tap because Cin % 4 == 0), hi = raw fp32, lo = a - trunc_tf32(a).
+      // never straddles a tap because Cin % 4 == 0) and split into the three bf16 planes.
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int HS = p.halo_slots, HW = p.halo_w;
       const int pix_bytes = c.Cin * 4;
-      uint32_t soff[4];
       int hp0[4];                                     // halo pixel of tap (0,0) for this thread's 4 output rows
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = r0 + 32 * i;
-        soff[i] = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
         hp0[i] = (row / p.tile_w) * c.stride * HW + (row % p.tile_w) * c.stride;
       }
       int stage = 0, slot = 0;
@@ -470,17 +318,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           for (int i = 0; i < 4; ++i)
             a[i] = k0 < p.K ? *reinterpret_cast<const float4*>(hb + (size_t)hp0[i] * pix_bytes + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+          unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 l;
-            l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
-            l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
-            l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
-            l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(hi + soff[i]) = a[i];                 // the tensor core drops the low 13 bits itself
-            *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
-          }
+          for (int i = 0; i < 4; ++i) store_split3(st, r0 + 32 * i, ch, a[i]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
@@ -491,10 +331,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         if (++slot == HS) { slot = 0; hphase ^= 1; }
       }
     } else if (MODE != 2) {
-      // cp.async pipeline: the 16 B pieces are copied global -> shared (zero-filled outside the image / past K) straight
-      // into their swizzled slot of the stage's `hi` slab, up to `depth` K-slabs ahead of the one being converted, so
-      // tens of KB per SM are in flight without holding registers.  Each thread then rewrites ITS OWN pieces in place as
-      // hi = rn_tf32(a) and stores lo = rn_tf32(a - hi) -- no cross-thread dependency, no extra barrier.
+      // cp.async pipeline: the 16 B fp32 pieces are copied global -> shared (zero-filled outside the image / past K) into the
+      // stage's a1|a2 area (same swizzled 128 B-row layout a TMA box would give), up to `depth` K-slabs ahead of the one
+      // being converted, so tens of KB per SM are in flight without holding registers.  Each thread then reads its own pieces
+      // back and -- after a __syncwarp, a warp covers whole rows -- overwrites the rows in place with the bf16 splits.
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
       const int depth = min(p.stages - 1, 3);
@@ -540,7 +380,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             tap_x = tap - tap_y * c.KS;
           }
           mbar_wait(smem_u32(&empty_bar[i_stage]), i_phase ^ 1);
-          const uint32_t dst = ring + (uint32_t)i_stage * 2u * TC_SLAB_BYTES;
+          const uint32_t dst = ring + (uint32_t)i_stage * (uint32_t)TC_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float* src = c.in;
@@ -568,24 +408,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
           default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
         }
-        unsigned char* hi = a_ring + (size_t)c_stage * 2 * TC_SLAB_BYTES;
+        unsigned char* st = a_ring + (size_t)c_stage * TC_STAGE_BYTES;
+        float4 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float4* ph = reinterpret_cast<float4*>(hi + soff[i]);
-          const float4 a = *ph;
-          float4 h, l;
-          if (p.raw_hi) {      // hi = what the tensor core will read: the value with the low 13 mantissa bits dropped
-            l.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-            l.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-            l.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-            l.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-          } else {
-            h.x = tf32_rn(a.x); h.y = tf32_rn(a.y); h.z = tf32_rn(a.z); h.w = tf32_rn(a.w);
-            l.x = tf32_rn(a.x - h.x); l.y = tf32_rn(a.y - h.y); l.z = tf32_rn(a.z - h.z); l.w = tf32_rn(a.w - h.w);
-            *ph = h;
-          }
-          *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + soff[i]) = l;
-        }
+        for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(st + soff[i]);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) store_split3(st, r0 + 32 * i, ch, a[i]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[c_stage]));
@@ -596,8 +425,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       // (tile_h + KS - 1) x (tile_w + KS - 1) x 32-channel halo of the INPUT arrives in a ring slot as ONE TMA tile
       // (cp.async.bulk.tensor.4d over the NHWC tensor, issued by the TMA warp; out-of-image pixels and channels past K
       // are zero-filled by the hardware = the conv padding).  Every producer thread computes the depthwise KS x KS
-      // (+ bias, act2) for 4 horizontally adjacent pixels x 4 channels from shared memory, splits hi/lo and writes the
-      // A stage.  With p.wstream the K-slab of the pointwise weights travels with the A stage (cp.async.bulk from L2).
+      // (+ bias, act2) for 4 horizontally adjacent pixels x 4 channels from shared memory, splits it into bf16 triples and
+      // writes the A stage.  With p.wstream the K-slab of the pointwise weights travels with the A stage (cp.async.bulk from L2).
       // The 8 producer warps form two groups of 4 that take alternate K-slabs (both A stages are then in progress at
       // once); inside a group every thread owns a patch of 2 rows x 4 pixels x 4 channels, so each halo row it loads
       // feeds two output rows -- the stage is bound by shared-memory reads, and this cuts them by ~40 %.
@@ -695,25 +524,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           for (int i = 0; i < 8; ++i) a[i] = act4(a[i], c.act2);
         }
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-        unsigned char* hi = a_ring + (size_t)stage * 2 * TC_SLAB_BYTES;
+        unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
         const int nst = p.dw_stride == 2 ? (valid2 ? 4 : 0) : (valid ? 8 : 0);
         {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             if (i >= nst) break;
             const int row = p.dw_stride == 2 ? arow2 + i : arow0 + (i >> 2) * TW + (i & 3);
-            const uint32_t so = (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4);
-            if (p.raw_hi) {          // the tensor core drops the low 13 mantissa bits of hi itself
-              float4 l;
-              l.x = a[i].x - __uint_as_float(__float_as_uint(a[i].x) & 0xFFFFE000u);
-              l.y = a[i].y - __uint_as_float(__float_as_uint(a[i].y) & 0xFFFFE000u);
-              l.z = a[i].z - __uint_as_float(__float_as_uint(a[i].z) & 0xFFFFE000u);
-              l.w = a[i].w - __uint_as_float(__float_as_uint(a[i].w) & 0xFFFFE000u);
-              *reinterpret_cast<float4*>(hi + so) = a[i];
-              *reinterpret_cast<float4*>(hi + TC_SLAB_BYTES + so) = l;
-            } else {
-              split_store(hi, hi + TC_SLAB_BYTES, row, ch, a[i]);
-            }
+            store_split3(st, row, ch, a[i]);
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -731,16 +549,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                       "r"((uint32_t)TC_SLAB_BYTES + (p.wstream ? 2u * w_slab_bytes : 0u)) : "memory");
+                       "r"((uint32_t)TC_P12_BYTES + (p.wstream ? w_slab_bytes : 0u)) : "memory");
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                       ::"r"(smem_u32(a_ring) + (uint32_t)stage * 2u * TC_SLAB_BYTES), "l"(&tmap), "r"(s * 32), "r"(tile * TC_BM), "r"(bar)
+                       ::"r"(smem_u32(a_ring) + (uint32_t)stage * (uint32_t)TC_STAGE_BYTES), "l"(&tmap), "r"(s * 32), "r"(tile * TC_BM), "r"(bar)
                        : "memory");
-          if (p.wstream) {          // K too long for a resident weight image: this K-slab of W (hi, lo) rides with the A tile
+          if (p.wstream) {          // K too long for a resident weight image: this K-slab of W (three splits) rides with the A tile
 #pragma unroll
-            for (int ps = 0; ps < 2; ++ps)
+            for (int q3 = 0; q3 < 3; ++q3)
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                           ::"r"(smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes), "l"(p.wimg + (((size_t)ps * p.nslab + s) * p.Npad + chunk_n0) * 32),
-                             "r"(w_slab_bytes), "r"(bar) : "memory");
+                           ::"r"(smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes),
+                             "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_split_bytes), "r"(bar) : "memory");
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -765,6 +583,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             : "memory");
         if (++slot == p.halo_slots) { slot = 0; hphase ^= 1; }
       }
+    } else if (p.wstream && lane == 0) {
+      // generic gather (cp.async producers) with a K too long for resident weights (the dense 3x3 convs of the YOLOLiteMS FPN,
+      // K = 9 * 196 ... 9 * 328): this thread streams the K-slab of W (three splits) that belongs to each A stage from L2
+      const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int it = 0; it < my_tiles; ++it)
+        for (int s = 0; s < p.nslab; ++s) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage's W slot are done
+          const uint32_t bar = smem_u32(&wfull_bar[stage]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_slab_bytes) : "memory");
+#pragma unroll
+          for (int q3 = 0; q3 < 3; ++q3)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes),
+                           "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_split_bytes), "r"(bar) : "memory");
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
     }
     __syncwarp();
   } else if (MODE == 2 && warp == TC_TMA_WARP) {
@@ -797,13 +633,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           // the MMAs that read this stage's A and W slots (item j - stages) are done: refill the W slot from L2
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * w_slab_bytes) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_slab_bytes) : "memory");
 #pragma unroll
-          for (int ps = 0; ps < 2; ++ps) {
-            const float* src = p.wimg + (((size_t)ps * p.nslab + i_s) * p.Npad + chunk_n0) * 32;
-            const uint32_t dst = smem_u32(w_hi) + (uint32_t)(stage * 2 + ps) * w_slab_bytes;
+          for (int q3 = 0; q3 < 3; ++q3) {
+            const float* src = p.wimg + (((size_t)i_s * 3 + q3) * p.Npad + chunk_n0) * 16;
+            const uint32_t dst = smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(w_slab_bytes), "r"(bar) : "memory");
+                         ::"r"(dst), "l"(src), "r"(w_split_bytes), "r"(bar) : "memory");
           }
         }
         if (++i_s == p.nslab) { i_s = 0; i_tile += gridDim.x; }
@@ -814,40 +650,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     __syncwarp();
   } else if (warp == TC_MMA_WARP) {
     // =============================== MMA issuer ===============================
-    // Two accumulators per tile: `main` takes Ahi*Whi, `corr` takes Alo*Whi + Ahi*Wlo.  The tensor core truncates its fp32
-    // accumulator on every instruction, which biases a long accumulation chain; keeping the (2^-11 smaller) correction
-    // terms in their own accumulator cuts the chain on the big one to K/8 steps.  The epilogue adds the two in fp32.
+    // Two accumulators per tile: `main` takes A1*W1 (16-bit products: most of them add to the accumulator without loss), `corr`
+    // the five 2^-8 ... 2^-16 smaller cross terms.  The tensor core truncates its fp32 accumulator, so the chain that carries the
+    // magnitude must be short and made of short products; the epilogue adds the two in fp32 (round to nearest).
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.Nc) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const uint32_t buf_stride = MODE == 3 ? 64u : (uint32_t)(2 * p.Nc);
+      const uint32_t buf_stride = (uint32_t)(2 * p.Nc);
       if (!p.wstream) mbar_wait(smem_u32(wres_bar), 0);          // the resident weight image has landed
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        if (MODE == 3) {            // five stem GEMM tiles (K = 32, N = 32) against the resident stem weight image
-          const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-          const uint32_t bs_hi = smem_u32(halo), bs_lo = bs_hi + 4096;
-          for (int j = 0; j < 5; ++j) {
-            mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t dm = tmem_base + (uint32_t)acc * buf_stride, dc = dm + 32;
-            mbar_wait(smem_u32(&full_bar[stage]), phase);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(a_ring + (size_t)stage * 2 * TC_SLAB_BYTES), a_lo = a_hi + TC_SLAB_BYTES;
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint32_t ko = (uint32_t)k4 * 32u;
-              mma_tf32(dc, make_desc(a_lo + ko), make_desc(bs_hi + ko), idesc_s, k4 > 0);
-              mma_tf32(dc, make_desc(a_hi + ko), make_desc(bs_lo + ko), idesc_s, 1);
-              mma_tf32(dm, make_desc(a_hi + ko), make_desc(bs_hi + ko), idesc_s, k4 > 0);
-            }
-            mma_commit(smem_u32(&empty_bar[stage]));
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
-            mma_commit(smem_u32(&tfull_bar[acc]));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          }
-        }
         mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_main = tmem_base + (uint32_t)acc * buf_stride;
@@ -856,23 +671,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_u32(a_ring + (size_t)stage * 2 * TC_SLAB_BYTES);
-          const uint32_t a_lo = a_hi + TC_SLAB_BYTES;
-          uint32_t b_hi = smem_u32(w_hi + (size_t)s * w_slab_bytes);
-          uint32_t b_lo = smem_u32(w_lo + (size_t)s * w_slab_bytes);
+          const uint32_t a12 = smem_u32(a_ring + (size_t)stage * TC_STAGE_BYTES);      // rows: [a1 (64 B) | a2 (64 B)], SWIZZLE_128B
+          const uint32_t a3 = a12 + (uint32_t)TC_P12_BYTES;                            // rows: a3 (64 B), SWIZZLE_64B
+          uint32_t b1 = smem_u32(w_base + (size_t)s * w_slab_bytes);
           if (p.wstream) {
-            // this stage's W slabs: MODE 2 waits for them here; in MODE 0 they share the A tile's barrier, which the
+            // this stage's W slab: MODES 1 / 2 wait for it here; in MODE 0 it shares the A tile's barrier, which the
             // producers have already waited on
-            if (MODE == 2) mbar_wait(smem_u32(&wfull_bar[stage]), phase);
-            b_hi = smem_u32(w_hi) + (uint32_t)(stage * 2) * w_slab_bytes;
-            b_lo = b_hi + w_slab_bytes;
+            if (MODE == 2 || MODE == 1) mbar_wait(smem_u32(&wfull_bar[stage]), phase);
+            b1 = smem_u32(w_base) + (uint32_t)stage * w_slab_bytes;
           }
-          const int ksteps = min(4, (p.K - s * 32 + 7) >> 3);
+          const uint32_t b2 = b1 + w_split_bytes, b3 = b2 + w_split_bytes;
+          const int ksteps = min(2, (p.K - s * 32 + 15) >> 4);
           for (int j = 0; j < ksteps; ++j) {
-            const uint32_t ko = (uint32_t)j * 32u;          // 8 fp32 = 32 B along K inside the 128 B swizzle row
-            mma_tf32(d_corr, make_desc(a_lo + ko), make_desc(b_hi + ko), idesc, first);
-            mma_tf32(d_corr, make_desc(a_hi + ko), make_desc(b_lo + ko), idesc, 1);
-            mma_tf32(d_main, make_desc(a_hi + ko), make_desc(b_hi + ko), idesc, first);
+            const uint32_t ko = (uint32_t)j * 32u;          // 16 bf16 = 32 B along K inside the swizzled row
+            mma_bf16(d_main, make_desc(a12 + ko), make_desc64(b1 + ko), idesc_2n, first);          // A1 x [W1|W2] -> [main|corr]
+            mma_bf16(d_corr, make_desc(a12 + 64u + ko), make_desc64(b1 + ko), idesc_n, 1);         // A2 x W1
+            mma_bf16(d_corr, make_desc(a12 + 64u + ko), make_desc64(b2 + ko), idesc_n, 1);         // A2 x W2
+            mma_bf16(d_corr, make_desc(a12 + ko), make_desc64(b3 + ko), idesc_n, 1);               // A1 x W3
+            mma_bf16(d_corr, make_desc64(a3 + ko), make_desc64(b1 + ko), idesc_n, 1);              // A3 x W1
             first = 1;
           }
           mma_commit(smem_u32(&empty_bar[stage]));           // frees this A stage once the MMAs have read it
@@ -902,13 +718,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
     int acc = p.epi2 ? grp : 0;
-    uint32_t acc_phase = 0, hphase = 0;
+    uint32_t acc_phase = 0;
     const int tile_step = p.epi2 ? 2 * (int)gridDim.x : (int)gridDim.x;
     for (int tile = blockIdx.x + (p.epi2 ? grp * (int)gridDim.x : 0); tile < tiles; tile += tile_step) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
-      const bool spatial = MODE >= 2 || (MODE == 1 && p.tma_a);   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
+      const bool spatial = MODE == 2 || (MODE == 1 && p.tma_a);   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
       const int rows_ok = spatial ? 32 : min(32, M - mw);      // rows of this warp inside the matrix
-      if (MODE != 3 && p.tma_out) {
+      if (p.tma_out) {
         // TMEM -> registers (lane = row) -> +bias, act -> SWIZZLE_128B staging tile (conflict-free 16 B stores) -> ONE TMA tensor
         // store per warp and 32-column block; rows / columns outside the tensor are clipped by the hardware
         int c1 = mw, c2 = 0, c3 = 0;
@@ -999,7 +815,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       if (spatial) {
         const int per_img = p.tiles_x * p.tiles_y;
         const int b = tile / per_img, rem = tile - b * per_img;
-        const int TW = MODE == 3 ? TC_TILE_W : p.tile_w, TH = MODE == 3 ? TC_TILE_H : p.tile_h;
+        const int TW = p.tile_w, TH = p.tile_h;
         const int y0 = (rem / p.tiles_x) * TH, x0 = (rem % p.tiles_x) * TW;
         int ry = (q * 32 + vr) / TW, rx = (q * 32 + vr) - ry * TW;      // rows vr + 4*it: step 4 pixels (TW % 4 == 0)
 #pragma unroll
@@ -1026,49 +842,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           while (ox >= c.Wout) { ox -= c.Wout; if (++oy == c.Hout) { oy = 0; if (b + 1 < c.B) ++b; } }
         }
       }
-      if (MODE == 3) {
-        // drain the five stem GEMM tiles into the shared-memory halo: bias + ReLU, zero outside the stem output
-        unsigned char* halb = halo + 8192;
-        const int per_img = p.tiles_x * p.tiles_y;
-        const int rem = tile % per_img;
-        const int sy0 = (rem / p.tiles_x) * TC_TILE_H * 2 - 1, sx0 = (rem % p.tiles_x) * TC_TILE_W * 2 - 1;
-        mbar_wait(smem_u32(halo_empty), hphase ^ 1);          // previous tile's slabs have been gathered
-        hphase ^= 1;
-        for (int j = 0; j < 5; ++j) {
-          mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * 64u;
-          uint32_t v[32], w[32];
-          tmem_ld32_nowait(ta, v);
-          tmem_ld32_nowait(ta + 32, w);
-          tmem_ld_wait();
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
-          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          const int pix = j * 128 + q * 32 + lane;
-          if (pix < S3_HALO_PIX) {
-            const int hy = pix / S3_HALO_W, hx = pix - hy * S3_HALO_W;
-            const int sy = sy0 + hy, sx = sx0 + hx;
-            const bool in_img = sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;
-#pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-              float4 o;
-              o.x = fmaxf(__uint_as_float(v[4 * g4 + 0]) + __uint_as_float(w[4 * g4 + 0]), 0.f);      // bias rides in the GEMM (k = 27)
-              o.y = fmaxf(__uint_as_float(v[4 * g4 + 1]) + __uint_as_float(w[4 * g4 + 1]), 0.f);
-              o.z = fmaxf(__uint_as_float(v[4 * g4 + 2]) + __uint_as_float(w[4 * g4 + 2]), 0.f);
-              o.w = fmaxf(__uint_as_float(v[4 * g4 + 3]) + __uint_as_float(w[4 * g4 + 3]), 0.f);
-              if (!in_img) o = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(halb + (size_t)pix * 128 + ((g4 ^ (pix & 7)) << 4)) = o;
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(halo_full));
-      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (MODE == 3 ? 64u : (uint32_t)(2 * p.Nc));
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
       for (int col = 0; col < p.Nc; col += 32) {
         const int wcols = min(32, p.Nc - col);                // 32, or 16 for the last block
         {
@@ -1226,7 +1002,7 @@ static void tc_pick_tile(int ks, int stride, int Hout, int Wout, TcPlan* pl) {
   pl->halo_bytes = pl->halo_pix * 128;
 }
 
-// MODE 2 with weights too large to stay resident next to the halo ring: one K-slab (hi, lo) of W per A stage, from L2
+// MODE 2 with weights too large to stay resident next to the halo ring: one K-slab (three splits) of W per A stage, from L2
 static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   (void)nslab;
   // N chunks of equal size Nc <= 128 (one CTA row per chunk; each repeats the depthwise stage): fewest chunks that fit
@@ -1234,7 +1010,7 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
     if ((Npad / 16) % nch) continue;
     const int Nc = Npad / nch;
     if (Nc > 128) continue;
-    const size_t fixed = (size_t)2 * (2 * TC_SLAB_BYTES + 2 * Nc * 128) + TC_AUX_BYTES + dw_bytes + 1024;
+    const size_t fixed = (size_t)2 * (TC_STAGE_BYTES + 3 * Nc * 64) + TC_AUX_BYTES + dw_bytes + 1024;
     if (fixed + 2 * (size_t)pl->halo_bytes > (size_t)TC_SMEM_BUDGET) continue;
     pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 1; pl->stages = 2;
     pl->halo_slots = 2;
@@ -1245,8 +1021,8 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
   return false;
 }
 
-// MODE 0 with TMA-fed A tiles and a K too long for a resident weight image at one N chunk: every stage carries its own
-// K-slab of W (hi, lo) next to the A tile.  Returns false when it does not fit.
+// MODE 0 with TMA-fed A tiles (or MODE 1, generic gather) and a K too long for a resident weight image at one N chunk: every
+// stage carries its own K-slab of W (three splits) next to the A tile.  Returns false when it does not fit.
 static bool tc_plan_stream0(int N, int anchors, int max_chunks, TcPlan* pl) {
   const int Npad = (N + 15) / 16 * 16;
   for (int nch = 1; nch < max_chunks; ++nch) {        // only if it needs fewer N chunks than the resident plan
@@ -1255,7 +1031,7 @@ static bool tc_plan_stream0(int N, int anchors, int max_chunks, TcPlan* pl) {
     if (Nc > 128) continue;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
     const size_t fixed = TC_AUX_BYTES + dense_bytes + 1024;
-    const size_t per_stage = (size_t)2 * TC_SLAB_BYTES + (size_t)2 * Nc * 128;
+    const size_t per_stage = (size_t)TC_STAGE_BYTES + (size_t)3 * Nc * 64;
     int stages = (int)((TC_SMEM_BUDGET - fixed) / per_stage);
     if (stages < 2) continue;
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
@@ -1280,18 +1056,12 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
   for (int nch = 1; nch <= 8; ++nch) {
     int Nc = ((Npad / 16 + nch - 1) / nch) * 16;
     if (Nc > 128) continue;                      // 2 buffers x (main + correction) accumulators x Nc <= 512 TMEM columns
-    const size_t wbytes = (size_t)2 * nslab * Nc * 128;
+    const size_t wbytes = (size_t)3 * nslab * Nc * 64;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
-    size_t fixed = wbytes + (mode == 3 ? TC_AUX_BYTES - 4 * (TC_STG_BYTES - 4608) : TC_AUX_BYTES) + dense_bytes + 1024;
+    size_t fixed = wbytes + TC_AUX_BYTES + dense_bytes + 1024;
     pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 0; pl->halo_slots = 0;
-    if (mode == 3) {                             // stem-output halo + input patch, 2 A stages
-      fixed += (size_t)8192 + S3_HALO_BYTES + S3_PATCH_BYTES + 2 * 2 * TC_SLAB_BYTES;
-      if (fixed > (size_t)TC_SMEM_BUDGET) continue;
-      pl->stages = 2; pl->smem = fixed;
-      return true;
-    }
     if (mode == 2) {                             // halo ring (2..4 slots) + depthwise weights, 2 A stages
-      fixed += dw_bytes + 2 * 2 * TC_SLAB_BYTES;
+      fixed += dw_bytes + 2 * TC_STAGE_BYTES;
       if (fixed + 2 * pl->halo_bytes > (size_t)TC_SMEM_BUDGET) continue;
       // splitting N over CTAs repeats the depthwise stage in every chunk: when the whole N fits one CTA's TMEM, streaming
       // the weight slabs (below) is cheaper than chunking
@@ -1301,22 +1071,24 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
       pl->stages = 2; pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
       return true;
     }
-    if (fixed + 2 * 2 * TC_SLAB_BYTES > (size_t)TC_SMEM_BUDGET) continue;
+    if (fixed + 2 * TC_STAGE_BYTES > (size_t)TC_SMEM_BUDGET) continue;
     // second epilogue group (MODE 0 + TMA, plain vector epilogue): four more transpose staging buffers, if 3 stages still fit
     const size_t epi2_bytes = (size_t)4 * TC_STG_BYTES;
     pl->epi2 = 0;
     if (want_epi2 && mode == 0 && dense_bytes == 0 && (N & 3) == 0 && anchors <= 1 &&
-        fixed + epi2_bytes + 3 * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) {
+        fixed + epi2_bytes + 3 * TC_STAGE_BYTES <= (size_t)TC_SMEM_BUDGET) {
       pl->epi2 = 1;
       fixed += epi2_bytes;
     }
-    int stages = (int)((TC_SMEM_BUDGET - fixed) / (2 * TC_SLAB_BYTES));
+    int stages = (int)((TC_SMEM_BUDGET - fixed) / TC_STAGE_BYTES);
     if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
-    pl->stages = stages; pl->smem = fixed + (size_t)stages * 2 * TC_SLAB_BYTES;
+    pl->stages = stages; pl->smem = fixed + (size_t)stages * TC_STAGE_BYTES;
     return true;
   }
   if (mode == 2 && (N & 3) == 0) return tc_plan_stream(nslab, Npad, dw_bytes, pl);
-  if (mode == 0) return tc_plan_stream0(N, anchors, 9, pl);        // needs the TMA-fed A path (checked at launch)
+  // MODE 0 needs the TMA-fed A path for streamed weights (checked at launch); MODE 1 (dense KxK with a long K, e.g. the 3x3
+  // convs of the YOLOLiteMS FPN) streams them next to its gathered A stages
+  if (mode == 0 || mode == 1) return tc_plan_stream0(N, anchors, 9, pl);
   return false;
 }
 
@@ -1391,9 +1163,8 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   p.c = c;
   p.wimg = wimg;
   p.mode = mode;
-  static const int raw_hi_env = [] { const char* e = getenv("YL_TC_RAWHI"); return e ? atoi(e) : 1; }();
-  p.raw_hi = raw_hi_env;
-  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;      // mode 3: c.Cin = 32 stem channels, KS = 3 -> 288
+  YL_REQUIRE(mode >= 0 && mode <= 2, "tcgen05 conv modes: 0 pointwise, 1 dense KxK, 2 depthwise -> pointwise");
+  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
   TcPlan pl;
@@ -1412,16 +1183,11 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   p.Nc = pl.Nc; p.nchunks = pl.nchunks; p.stages = pl.stages; p.halo_slots = pl.halo_slots; p.wstream = pl.wstream;
   p.tile_w = pl.tile_w; p.tile_h = pl.tile_h; p.halo_w = pl.halo_w; p.halo_pix = pl.halo_pix; p.halo_bytes = pl.halo_bytes;
   p.dw_stride = mode == 2 ? c.stride : 1;
-  p.stg_stride = mode == 3 ? 4608 : TC_STG_BYTES;
+  p.stg_stride = TC_STG_BYTES;
   p.dense_epi = tc_dense_epi(c.Cout, c.anchors, p.Nc, p.nchunks) ? 1 : 0;
   YL_REQUIRE((c.Cin & 3) == 0, "tcgen05 conv needs Cin % 4 == 0");
   p.M = (long long)c.B * c.Hout * c.Wout;
   p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
-  if (mode == 3) {
-    YL_REQUIRE(c.Cin == 32 && c.KS == 3 && c.stride == 2 && c.w2, "fused stem kernel: 3x3 s2 stem with 32 channels -> 3x3 s2 conv");
-    p.Hs = (c.Hin + 2 - 3) / 2 + 1;
-    p.Ws = (c.Win + 2 - 3) / 2 + 1;
-  }
   // MODE 1 with a small Cin: whole-Cin halo tiles by TMA + shared-memory im2col (see the producer branch)
   size_t smem_override = 0;
   if (mode == 1 && tma_env && pl.nchunks == 1 && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (c.Cin & 3) == 0 && c.Cin <= 64 &&
@@ -1430,26 +1196,26 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
     const int hw_ = (tw - 1) * c.stride + c.KS, hh_ = (th - 1) * c.stride + c.KS;
     const size_t hexact = (size_t)hw_ * hh_ * c.Cin * 4;
     const size_t hbytes = (hexact + 127) / 128 * 128;
-    const size_t fixed = (size_t)2 * p.nslab * pl.Nc * 128 + TC_AUX_BYTES + 1024;
-    if (hw_ <= 256 && hh_ <= 256 && fixed + 2 * hbytes + 2 * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) {
+    const size_t fixed = (size_t)3 * p.nslab * pl.Nc * 64 + TC_AUX_BYTES + 1024;
+    if (!pl.wstream && hw_ <= 256 && hh_ <= 256 && fixed + 2 * hbytes + 2 * TC_STAGE_BYTES <= (size_t)TC_SMEM_BUDGET) {
       p.tma_a = 1;
       pl.epi2 = 0;
       p.tile_w = tw; p.tile_h = th; p.halo_w = hw_; p.halo_pix = hw_ * hh_; p.halo_bytes = (int)hbytes; p.halo_tx = (int)hexact;
       p.halo_slots = 2;
-      int stages = (int)((TC_SMEM_BUDGET - fixed - 2 * hbytes) / (2 * TC_SLAB_BYTES));
+      int stages = (int)((TC_SMEM_BUDGET - fixed - 2 * hbytes) / TC_STAGE_BYTES);
       p.stages = stages > TC_MAX_STAGES ? TC_MAX_STAGES : stages;
-      if (fixed + 3 * hbytes + (size_t)p.stages * 2 * TC_SLAB_BYTES <= (size_t)TC_SMEM_BUDGET) p.halo_slots = 3;
-      smem_override = fixed + (size_t)p.halo_slots * hbytes + (size_t)p.stages * 2 * TC_SLAB_BYTES;
+      if (fixed + 3 * hbytes + (size_t)p.stages * TC_STAGE_BYTES <= (size_t)TC_SMEM_BUDGET) p.halo_slots = 3;
+      smem_override = fixed + (size_t)p.halo_slots * hbytes + (size_t)p.stages * TC_STAGE_BYTES;
       p.tiles_x = (c.Wout + tw - 1) / tw;
       p.tiles_y = (c.Hout + th - 1) / th;
       p.num_tiles = c.B * p.tiles_x * p.tiles_y;
       p.dense_epi = 0;
     }
   }
-  if (mode >= 2) {
-    YL_REQUIRE(!c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (mode == 2 || !c.res), "fused depthwise/stem epilogue takes no upsample/head layout");
-    YL_REQUIRE(mode == 3 || ((c.stride == 1 || c.stride == 2) && c.w2 && c.Hout == (c.Hin + 2 * (c.KS / 2) - c.KS) / c.stride + 1 &&
-                             c.Wout == (c.Win + 2 * (c.KS / 2) - c.KS) / c.stride + 1), "fused depthwise -> pointwise: depthwise stride 1 or 2");
+  if (mode == 2) {
+    YL_REQUIRE(!c.up && c.anchors <= 1 && (c.Cout & 3) == 0, "fused depthwise epilogue takes no upsample/head layout");
+    YL_REQUIRE((c.stride == 1 || c.stride == 2) && c.w2 && c.Hout == (c.Hin + 2 * (c.KS / 2) - c.KS) / c.stride + 1 &&
+               c.Wout == (c.Win + 2 * (c.KS / 2) - c.KS) / c.stride + 1, "fused depthwise -> pointwise: depthwise stride 1 or 2");
     p.tiles_x = (c.Wout + p.tile_w - 1) / p.tile_w;
     p.tiles_y = (c.Hout + p.tile_h - 1) / p.tile_h;
     p.num_tiles = c.B * p.tiles_x * p.tiles_y;
@@ -1459,7 +1225,6 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   YL_REQUIRE(!c.up || (long long)c.B * c.Hu * c.Wu * c.Cout < (1ll << 31), "upsample source too large for 32-bit offsets");
   int cols = 32;
   while (cols < 4 * p.Nc) cols <<= 1;
-  if (mode == 3) { YL_REQUIRE(p.Nc <= 32, "fused stem kernel: N chunk <= 32"); cols = 128; }
   p.tmem_cols = cols;
   const size_t smem = smem_override ? smem_override : pl.smem;
   {
@@ -1470,7 +1235,6 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
           YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<2, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          YL_CHECK_CUDA(cudaFuncSetAttribute(tc_conv_kernel<3, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
           return 0;
         }))
       return rc;
@@ -1503,7 +1267,7 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   memset(&omap, 0, sizeof(omap));
   static const int tmaout_env = [] { const char* e = getenv("YL_TC_TMAOUT"); return e ? atoi(e) : 1; }();
   const bool spatial = mode == 2 || (mode == 1 && p.tma_a);
-  if (tmaout_env && mode != 3 && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && (!c.up || (mode == 0 && (reinterpret_cast<uintptr_t>(c.up) & 15) == 0)) && c.Cout >= 32 &&
+  if (tmaout_env && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && (!c.up || (mode == 0 && (reinterpret_cast<uintptr_t>(c.up) & 15) == 0)) && c.Cout >= 32 &&
       (p.nchunks == 1 || (p.Nc & 31) == 0) && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (!spatial || 32 % p.tile_w == 0)) {
     int rc;
     if (spatial) {
@@ -1529,8 +1293,7 @@ int tc_launch(const TcLaunch& L, cudaStream_t st, int pdl) {
   if (mode == 0) e = launch_ex(tc_conv_kernel<0, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
   else if (mode == 1) e = launch_ex(tc_conv_kernel<1, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
   else if (mode == 2 && L.ks == 3) e = launch_ex(tc_conv_kernel<2, 3>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
-  else if (mode == 2) e = launch_ex(tc_conv_kernel<2, 5>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
-  else e = launch_ex(tc_conv_kernel<3, 0>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
+  else e = launch_ex(tc_conv_kernel<2, 5>, L.grid, TC_THREADS, L.smem, st, pdl, L.p, L.tmap, L.omap);
   YL_CHECK_CUDA(e);
   return 0;
 }

@@ -153,33 +153,6 @@ def _gemm_w(w: np.ndarray) -> np.ndarray:
     return out
 
 
-def tf32_rn(x: np.ndarray) -> np.ndarray:
-    """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits) -- same bit trick as the kernel's producers."""
-    u = np.ascontiguousarray(x, np.float32).view(np.uint32)
-    return ((u + np.uint32(0x1000)) & np.uint32(0xFFFFE000)).view(np.float32)
-
-
-def tc_image(wm: np.ndarray, n_out: int) -> np.ndarray:
-    """tcgen05 weight image of a GEMM matrix wm [K][>=n_out] (fp64, BN folded): [2 (hi,lo)][ceil(K/32)][ceil16(N)][32] fp32.
-
-    hi = tf32_rn(w), lo = tf32_rn(w - hi).  Each K-slab is the K-major SWIZZLE_128B canonical UMMA layout:
-    row n holds 32 consecutive k as 8 chunks of 16 B, chunk c stored at position c ^ (n % 8)."""
-    K = wm.shape[0]
-    nslab, npad = (K + 31) // 32, (n_out + 15) // 16 * 16
-    w = np.zeros((nslab * 32, npad), np.float32)
-    w[:K, :n_out] = wm[:, :n_out].astype(np.float32)
-    hi = tf32_rn(w)
-    lo = tf32_rn((w - hi).astype(np.float32))
-    out = np.empty((2, nslab, npad, 8, 4), np.float32)
-    n = np.arange(npad)
-    for pi, x in enumerate((hi, lo)):
-        t = x.reshape(nslab, 8, 4, npad).transpose(0, 3, 1, 2)          # [slab][n][chunk][4]
-        dst = out[pi]
-        for c in range(8):
-            dst[:, n, c ^ (n % 8), :] = t[:, n, c, :]
-    return out.reshape(-1)
-
-
 def bf16_split3(x: np.ndarray):
     """x (fp32) -> three uint16 arrays of bf16 bit patterns with x ~= b1 + b2 + b3 (each round-to-nearest-even), the
     error-compensated operand format of the fused stem kernel (csrc/stem_kernel.cu)."""
@@ -223,6 +196,25 @@ def _sw64_rows(m: np.ndarray) -> np.ndarray:
     for c in range(4):
         out[r, c ^ ((r >> 1) & 3), :] = t[r, c, :]
     return out.reshape(rows, 32)
+
+
+def tc_image(wm: np.ndarray, n_out: int) -> np.ndarray:
+    """tcgen05 weight image of a GEMM matrix wm [K][>=n_out] (fp64, BN folded) for csrc/tc_gemm.cu, as float32 words (two bf16
+    per word, bits preserved): [ceil(K/32) slabs][3 splits][ceil16(N) rows][32 k].
+
+    w = w1 + w2 + w3 with bf16 splits taken in float64 (24 bits kept).  Each (slab, split) block is the K-major SWIZZLE_64B
+    canonical UMMA layout: row n holds 32 consecutive k as four 16 B chunks, chunk c stored at position c ^ ((n >> 1) & 3);
+    the three splits of a slab are adjacent so that [W1 | W2] is one B operand of N = 2 * rows."""
+    K = wm.shape[0]
+    nslab, npad = (K + 31) // 32, (n_out + 15) // 16 * 16
+    w = np.zeros((nslab * 32, npad), np.float64)
+    w[:K, :n_out] = wm[:, :n_out]
+    out = np.empty((nslab, 3, npad, 32), np.uint16)
+    for q, sp in enumerate(bf16_split3_f64(w)):
+        t = sp.reshape(nslab, 32, npad).transpose(0, 2, 1)               # [slab][n][k]
+        for sl in range(nslab):
+            out[sl, q] = _sw64_rows(np.ascontiguousarray(t[sl]))
+    return out.reshape(-1).view(np.float32)
 
 
 def stem_u8_matrix(ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
@@ -367,7 +359,7 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
                 pw_blob = np.concatenate([wq.T.reshape(-1), bq.reshape(-1)])          # [k][n] then bias[n]
             x = emit(L.OP_STEM2, None, c1, 4, k=3, stride=2, act=L.ACT_RELU, w=w1m, b2=pw_blob, act2=(L.ACT_RELU if pw_blob is not None else L.ACT_NONE),
                      w3=stem2_image(w1m, int(w1.shape[0]), ws, b0) if int(w1.shape[0]) <= 32 else None,
-                     b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1), tc_image(np.concatenate([ws, b0.reshape(1, -1)]), stem_c).astype(np.float64)]), k2=stem_c)
+                     b=b1, w2=np.concatenate([ws.reshape(-1), b0.reshape(-1)]), k2=stem_c)
             feats = [_T(-1, stem_c, 2)]
             red = 4
         else:
