@@ -217,3 +217,22 @@ def test_predict_batch_uses_one_graph_launch_per_call(tmp_path):
     assert sum(len(r["index"]) for r in ref) > 0
     for a, r in zip(first, ref):
         assert np.array_equal(np.sort(a["index"].cpu().numpy()), np.sort(r["index"]))
+
+
+def test_sustained_back_to_back_forwards_do_not_deadlock():
+    """600 forwards of the benchmark configuration back to back (PDL on): regression test for a 1-in-1000 mbarrier phase-aliasing
+    deadlock in the fused depthwise -> pointwise kernel (odd halo ring depth with two alternating producer groups); a protocol
+    error traps, which surfaces here as a CUDA error."""
+    ck = synth_ckpt("edge_n", 80, 640)
+    eng = _engine(ck)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn((64, 3, 640, 640), device="cuda", generator=g)
+    outs = eng(x)
+    first = [o.clone() for o in outs]
+    for _ in range(600):
+        eng.forward(x, out=outs)
+    torch.cuda.synchronize()
+    import yololite_b200 as y
+    assert y.lib().yl_stat(b"trap_word10") == 0
+    for a, b in zip(outs, first):
+        assert torch.equal(a, b) and bool(torch.isfinite(a).all())

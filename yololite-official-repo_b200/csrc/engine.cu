@@ -23,6 +23,16 @@ std::atomic<long long> g_tc_launches{0}, g_simt_launches{0}, g_post_launches{0},
     g_prepares{0};
 void set_error(const std::string& msg) { g_err = msg; }
 
+unsigned long long* debug_words() {
+  static unsigned long long* w = [] {
+    unsigned long long* h = nullptr;
+    if (cudaHostAlloc(&h, 32 * sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return (unsigned long long*)nullptr; }
+    memset(h, 0, 32 * sizeof(unsigned long long));
+    return h;
+  }();
+  return w;
+}
+
 struct BufShape {
   int H = 0, W = 0, C = 0;
   size_t off = 0, bytes = 0;
@@ -169,6 +179,8 @@ static int launch_simt(const yl_op& op, const ConvParams& p, cudaStream_t st) {
 }
 
 static const int g_old_stem = [] { const char* e = getenv("YL_OLD_STEM"); return e ? atoi(e) : 0; }();
+static const int g_sync_each = [] { const char* e = getenv("YL_SYNC_EACH"); return e ? atoi(e) : 0; }();      // diagnostics: sync + check after every op
+static const int g_pdl_env = [] { const char* e = getenv("YL_PDL"); return e ? atoi(e) : 1; }();      // YL_PDL=0: diagnostics, never use PDL
 
 // YL_OP_STEM2 when the fused bf16 kernel cannot take the shape (W % 4 != 0, more than 32 conv2 channels ...): conv_stem on the
 // fp32 SIMT kernel into `tmp_stem` [B,Hs,Ws,32], the 3x3 s2 conv as an ordinary dense conv, then the fused pointwise conv (timm
@@ -394,7 +406,7 @@ struct CallArgs {
 static int enqueue_ops(yl_engine* e, const CallArgs& a, cudaStream_t st, cudaEvent_t* ev) {
   if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[0], st));
   auto bufptr = [&](int id) -> float* { return reinterpret_cast<float*>(e->arena + e->bufs[id].off); };
-  const int pdl = ev ? 0 : e->pdl;
+  const int pdl = (ev || !g_pdl_env) ? 0 : e->pdl;
   for (size_t i = 0; i < e->ops.size(); ++i) {
     const yl_op& op = e->ops[i];
     const float* in = op.src == YL_SRC_INPUT ? a.x : op.src <= YL_SRC_FEATURE(0) ? a.feats[YL_FEATURE_INDEX(op.src)] : bufptr(op.src);
@@ -404,6 +416,14 @@ static int enqueue_ops(yl_engine* e, const CallArgs& a, cudaStream_t st, cudaEve
     if (int rc = launch_cached(e, (int)i, in, op.src == YL_SRC_INPUT ? a.x_u8 : nullptr, op.res >= 0 ? bufptr(op.res) : nullptr,
                                op.up >= 0 ? bufptr(op.up) : nullptr, outp, st, pdl))
       return rc;
+    if (g_sync_each) {
+      const cudaError_t se = cudaStreamSynchronize(st);
+      if (se != cudaSuccess) {
+        set_error("op " + std::to_string(i) + " (kind " + std::to_string(op.kind) + ", " + std::to_string(op.cin) + "->" + std::to_string(op.cout) +
+                  ", k" + std::to_string(op.k) + "/" + std::to_string(op.k2) + ") failed: " + cudaGetErrorString(se));
+        return -2;
+      }
+    }
     if (ev) YL_CHECK_CUDA(cudaEventRecord(ev[i + 1], st));
   }
   if (a.detect) {
@@ -489,6 +509,7 @@ long long yl_stat(const char* key) {
   if (!std::strcmp(key, "graph_launches")) return yl::g_graph_launches;
   if (!std::strcmp(key, "graph_captures")) return yl::g_graph_captures;
   if (!std::strcmp(key, "prepares")) return yl::g_prepares;
+  if (!std::strncmp(key, "trap_word", 9)) { unsigned long long* w = yl::debug_words(); const int i = atoi(key + 9) & 31; return w ? (long long)w[i] : 0; }
   return -1;
 }
 int yl_abi_version(void) { return YL_ABI_VERSION; }

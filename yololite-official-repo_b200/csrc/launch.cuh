@@ -69,6 +69,7 @@ struct TcParams {
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span
   long long M;
   int num_tiles;
+  unsigned long long* dbg;   // mapped host memory: post-mortem word written before a protocol-error trap (engine.cu: debug_words)
 };
 
 struct TcLaunch {
@@ -78,6 +79,7 @@ struct TcLaunch {
   size_t smem;
   int ks;              // depthwise kernel size of MODE 2
 };
+unsigned long long* debug_words();      // 8 words of mapped pinned host memory (process-wide), zero when no kernel trapped
 int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, TcLaunch* L);
 int tc_launch(const TcLaunch& L, cudaStream_t st, int pdl);
 

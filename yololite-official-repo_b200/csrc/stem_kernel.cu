@@ -123,7 +123,6 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  pdl_launch_dependents();
 
   // ---- shared memory carve-up
   const int w2_bytes = 27 * p.N2 * 64;                              // conv2 weights: 3 splits x 9 taps x N2 rows x 64 B
@@ -175,6 +174,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
   const int per_img = p.tiles_x * p.tiles_y;
+  pdl_launch_dependents();      // after the TMEM allocation (see tc_gemm.cu)
   pdl_wait();      // the prologue above read only weights; the network input / output buffers are touched from here on
   // TMEM columns: stem ring slot r: [96r, 96r + 96) = main | corr | corr (32 each); conv2 buffer b: 288 + 96b + {0, N2, 2*N2}
   constexpr uint32_t ACC2_COL = S2_ACC2_COL;

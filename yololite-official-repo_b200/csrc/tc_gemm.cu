@@ -63,7 +63,7 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, volatile unsigned long long* dbg = nullptr, uint32_t tag = 0) {
   uint32_t ok = 0;
   for (uint32_t spin = 0; !ok; ++spin) {
     asm volatile(
@@ -73,7 +73,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity), "r"(2000u)      // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
-    if (spin > (1u << 22)) asm volatile("trap;");   // protocol error: fail loudly, never hang the device
+    if (spin > (1u << 22)) {                        // protocol error: fail loudly, never hang the device
+      if (dbg) {      // post-mortem word in mapped host memory: tag | parity | warp | block | barrier address
+        dbg[tag & 31u] = ((unsigned long long)tag << 56) | ((unsigned long long)(parity & 1u) << 55) | ((unsigned long long)(threadIdx.x >> 5) << 48) |
+                 ((unsigned long long)(blockIdx.x & 0xFFFFu) << 32) | (unsigned long long)bar;
+        __threadfence_system();
+        for (int w = 0; w < 100; ++w) __nanosleep(1000000);      // let the other stuck waiters record their words too
+      }
+      asm volatile("trap;");
+    }
   }
 }
 
@@ -165,7 +173,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const ConvParams& c = p.c;
   const int M = (int)p.M;
-  pdl_launch_dependents();      // the next kernel's prologue may overlap this kernel (it waits for our completion before reading)
 
   // ---- shared memory carve-up (all slabs 1024 B aligned)
   // weights of one K-slab: three bf16 splits x Nc rows x 64 B (SWIZZLE_64B, K-major): [W1 | W2 | W3], so that [W1|W2] is one
@@ -251,6 +258,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   const int tiles = p.num_tiles;
+  // PDL trigger AFTER this CTA holds its tensor memory: the next kernel's CTAs may now become resident and run their own
+  // prologue while this kernel works (they wait for our completion before reading activations).  Triggering before the TMEM
+  // allocation could let a dependent CTA grab columns first and then block this CTA in tcgen05.alloc for ever.
+  pdl_launch_dependents();
   // everything above touched only constant data (weights, biases) and this CTA's shared memory / TMEM: with PDL it overlapped
   // the previous kernel's tail.  From here on activations written by earlier kernels are read.
   pdl_wait();
@@ -272,7 +283,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < total; ++j) {
-        mbar_wait(smem_u32(&wfull_bar[stage]), phase);
+        mbar_wait(smem_u32(&wfull_bar[stage]), phase, p.dbg, 1u);
         unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
         for (int ps = 0; ps < npass; ++ps) {
           float4 a[4];
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       int stage = 0, slot = 0;
       uint32_t phase = 0, hphase = 0;
       for (int it = 0; it < my_tiles; ++it) {
-        mbar_wait(smem_u32(&hfull_bar[slot]), hphase);            // this tile's halo has landed
+        mbar_wait(smem_u32(&hfull_bar[slot]), hphase, p.dbg, 2u);            // this tile's halo has landed
         const unsigned char* hb = halo + (size_t)slot * p.halo_bytes;
         for (int s = 0; s < p.nslab; ++s) {
           const int k0 = s * 32 + ch * 4;
@@ -317,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             a[i] = k0 < p.K ? *reinterpret_cast<const float4*>(hb + (size_t)hp0[i] * pix_bytes + toff) : make_float4(0.f, 0.f, 0.f, 0.f);
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 3u);
           unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) store_split3(st, r0 + 32 * i, ch, a[i]);
@@ -379,7 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             tap_y = tap / c.KS;
             tap_x = tap - tap_y * c.KS;
           }
-          mbar_wait(smem_u32(&empty_bar[i_stage]), i_phase ^ 1);
+          mbar_wait(smem_u32(&empty_bar[i_stage]), i_phase ^ 1, p.dbg, 4u);
           const uint32_t dst = ring + (uint32_t)i_stage * (uint32_t)TC_STAGE_BYTES;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -449,7 +460,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       for (int j = grp; j < total; j += 2) {
         const int c_slot = j % HS, c_s = j % p.nslab, stage = j & 1;           // MODE 2 runs with 2 A stages
         const uint32_t hphase = (uint32_t)(j / HS) & 1u, phase = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(smem_u32(&hfull_bar[c_slot]), hphase);          // this item's halo tile has landed
+        mbar_wait(smem_u32(&hfull_bar[c_slot]), hphase, p.dbg, 5u);          // this item's halo tile has landed
         float4 a[8];                                              // [row 0: 4 pixels][row 1: 4 pixels]
         if (p.dw_stride == 2) {
           // stride 2: the tile is at most 64 output pixels (rows 64..127 of the MMA tile are unused); a thread owns ONE row of
@@ -523,7 +534,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
           for (int i = 0; i < 8; ++i) a[i] = act4(a[i], c.act2);
         }
-        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 6u);
         unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
         const int nst = p.dw_stride == 2 ? (valid2 ? 4 : 0) : (valid ? 8 : 0);
         {
@@ -546,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         for (int s = 0; s < p.nslab; ++s) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage are done
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 7u);          // the MMAs that read this stage are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
                        "r"((uint32_t)TC_P12_BYTES + (p.wstream ? w_slab_bytes : 0u)) : "memory");
@@ -574,7 +585,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const int b = tile / per_img, rem = tile - b * per_img;
         const int y0 = (rem / p.tiles_x) * p.tile_h * c.stride - c.pad, x0 = (rem % p.tiles_x) * p.tile_w * c.stride - c.pad;
-        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1);
+        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1, p.dbg, 8u);
         const uint32_t bar = smem_u32(&hfull_bar[slot]);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.halo_tx) : "memory");
         asm volatile(
@@ -591,7 +602,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       uint32_t phase = 0;
       for (int it = 0; it < my_tiles; ++it)
         for (int s = 0; s < p.nslab; ++s) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);          // the MMAs that read this stage's W slot are done
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 9u);          // the MMAs that read this stage's W slot are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_slab_bytes) : "memory");
 #pragma unroll
@@ -620,7 +631,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           y0 = (rem / p.tiles_x) * p.tile_h * p.dw_stride - PAD;
           x0 = (rem % p.tiles_x) * p.tile_w * p.dw_stride - PAD;
         }
-        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1);          // all producer warps are done with item j - HS
+        mbar_wait(smem_u32(&hempty_bar[slot]), hphase ^ 1, p.dbg, 10u);          // all producer warps are done with item j - HS
         {
           const uint32_t bar = smem_u32(&hfull_bar[slot]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)p.halo_bytes) : "memory");
@@ -631,7 +642,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         }
         if (p.wstream) {
           // the MMAs that read this stage's A and W slots (item j - stages) are done: refill the W slot from L2
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 11u);
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_slab_bytes) : "memory");
 #pragma unroll
@@ -661,15 +672,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t buf_stride = (uint32_t)(2 * p.Nc);
-      if (!p.wstream) mbar_wait(smem_u32(wres_bar), 0);          // the resident weight image has landed
+      if (!p.wstream) mbar_wait(smem_u32(wres_bar), 0, p.dbg, 12u);          // the resident weight image has landed
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1);
+        mbar_wait(smem_u32(&tempty_bar[acc]), acc_phase ^ 1, p.dbg, 13u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_main = tmem_base + (uint32_t)acc * buf_stride;
         const uint32_t d_corr = d_main + (uint32_t)p.Nc;
         uint32_t first = 0;
         for (int s = 0; s < p.nslab; ++s) {
-          mbar_wait(smem_u32(&full_bar[stage]), phase);
+          mbar_wait(smem_u32(&full_bar[stage]), phase, p.dbg, 14u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a12 = smem_u32(a_ring + (size_t)stage * TC_STAGE_BYTES);      // rows: [a1 (64 B) | a2 (64 B)], SWIZZLE_128B
           const uint32_t a3 = a12 + (uint32_t)TC_P12_BYTES;                            // rows: a3 (64 B), SWIZZLE_64B
@@ -677,7 +688,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           if (p.wstream) {
             // this stage's W slab: MODES 1 / 2 wait for it here; in MODE 0 it shares the A tile's barrier, which the
             // producers have already waited on
-            if (MODE == 2 || MODE == 1) mbar_wait(smem_u32(&wfull_bar[stage]), phase);
+            if (MODE == 2 || MODE == 1) mbar_wait(smem_u32(&wfull_bar[stage]), phase, p.dbg, 15u);
             b1 = smem_u32(w_base) + (uint32_t)stage * w_slab_bytes;
           }
           const uint32_t b2 = b1 + w_split_bytes, b3 = b2 + w_split_bytes;
@@ -745,7 +756,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           const int oy = rem / c.Wout, ox = rem - oy * c.Wout;
           up_row = c.up + ((size_t)(b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N + chunk_n0;
         }
-        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+        mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.dbg, 16u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
         for (int col = 0; col < p.Nc; col += 32) {
@@ -842,7 +853,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           while (ox >= c.Wout) { ox -= c.Wout; if (++oy == c.Hout) { oy = 0; if (b + 1 < c.B) ++b; } }
         }
       }
-      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
+      mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.dbg, 17u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
       for (int col = 0; col < p.Nc; col += 32) {
@@ -1013,8 +1024,11 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
     const size_t fixed = (size_t)2 * (TC_STAGE_BYTES + 3 * Nc * 64) + TC_AUX_BYTES + dw_bytes + 1024;
     if (fixed + 2 * (size_t)pl->halo_bytes > (size_t)TC_SMEM_BUDGET) continue;
     pl->Nc = Nc; pl->nchunks = nch; pl->wstream = 1; pl->stages = 2;
-    pl->halo_slots = 2;
-    while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
+    // The ring depth must be EVEN: the two producer groups take alternate K-slabs, so with an even depth a slot always belongs
+    // to the same group and a group's wait for round r of a slot follows its own round r-1.  With 3 slots a group could reach
+    // round r while the OTHER group's round r-1 load was still in flight, and its parity wait on the not-yet-flipped mbarrier
+    // passed spuriously (phase aliasing: ~1 deadlock per 1000 launches, found with the post-mortem words of mbar_wait).
+    pl->halo_slots = fixed + 4 * (size_t)pl->halo_bytes <= (size_t)TC_SMEM_BUDGET ? 4 : 2;
     pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
     return true;
   }
@@ -1066,8 +1080,7 @@ static bool tc_plan(int K, int N, int anchors, int mode, int dw_ks, int Hout, in
       // splitting N over CTAs repeats the depthwise stage in every chunk: when the whole N fits one CTA's TMEM, streaming
       // the weight slabs (below) is cheaper than chunking
       if (nch > 1 && Npad <= 128 && (N & 3) == 0 && tc_plan_stream(nslab, Npad, dw_bytes, pl)) return true;
-      pl->halo_slots = 2;
-      while (pl->halo_slots < TC_MAX_HALO_SLOTS && fixed + (size_t)(pl->halo_slots + 1) * pl->halo_bytes <= (size_t)TC_SMEM_BUDGET) ++pl->halo_slots;
+      pl->halo_slots = fixed + 4 * (size_t)pl->halo_bytes <= (size_t)TC_SMEM_BUDGET ? 4 : 2;      // even: see tc_plan_stream
       pl->stages = 2; pl->smem = fixed + (size_t)pl->halo_slots * pl->halo_bytes;
       return true;
     }
@@ -1163,6 +1176,7 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   p.c = c;
   p.wimg = wimg;
   p.mode = mode;
+  p.dbg = debug_words();
   YL_REQUIRE(mode >= 0 && mode <= 2, "tcgen05 conv modes: 0 pointwise, 1 dense KxK, 2 depthwise -> pointwise");
   p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
   p.nslab = (p.K + 31) / 32;

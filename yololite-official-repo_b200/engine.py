@@ -187,7 +187,8 @@ class YoloLiteB200:
                outputs=None, packed: Optional[torch.Tensor] = None):
         """tools/infer.py:456-493 for a batch.  x: fp32 [B,3,H,W] normalised, or uint8 [B,H,W,3] BGR (no-resize image entry).
         Returns (boxes [B,cap,4], scores [B,cap], classes i64, index i64, counts i32) -- pass `outputs` (same tuple) to reuse
-        buffers -- or fills `packed` [B,cap+1,6] (see yl_postprocess_ex) when given."""
+        buffers.  `packed` [B,cap+1,6] (see yl_postprocess_ex) is filled too when given; with `packed` and no `outputs` only the
+        payload is written and returned."""
         if self.from_features:
             raise RuntimeError("detect() needs the full network")
         u8 = x.dtype == torch.uint8
@@ -198,17 +199,17 @@ class YoloLiteB200:
         H, W = (int(x.shape[1]), int(x.shape[2])) if u8 else (int(x.shape[2]), int(x.shape[3]))
         dev = x.device
         ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        bx = sc = cl = ix = cn = None
         if packed is not None:
             if not (packed.is_cuda and packed.dtype == torch.float32 and tuple(packed.shape) == (B, cap + 1, 6) and packed.is_contiguous()):
                 raise ValueError(f"packed must be a contiguous CUDA float32 tensor of shape {(B, cap + 1, 6)}")
-            bx = sc = cl = ix = cn = None
-        elif outputs is not None:
+        if outputs is not None:
             bx, sc, cl, ix, cn = outputs
             want = (((B, cap, 4), torch.float32), ((B, cap), torch.float32), ((B, cap), torch.int64), ((B, cap), torch.int64), ((B,), torch.int32))
             for t, (shp, dt) in zip(outputs, want):
                 if not (t.is_cuda and t.dtype == dt and tuple(t.shape) == shp and t.is_contiguous() and t.device.index == self._dev_index):
                     raise ValueError(f"output buffer must be contiguous CUDA {dt} of shape {shp}")
-        else:
+        elif packed is None:
             bx = torch.empty((B, cap, 4), device=dev, dtype=torch.float32)
             sc = torch.empty((B, cap), device=dev, dtype=torch.float32)
             cl = torch.empty((B, cap), device=dev, dtype=torch.int64)
@@ -218,7 +219,7 @@ class YoloLiteB200:
                                          float(iou), int(max_det or 0), int(cap), ptr(bx), ptr(sc), ptr(cl), ptr(ix), ptr(cn), ptr(packed),
                                          _stream_ptr(dev)))
         self._last_detect_B = B
-        return packed if packed is not None else (bx, sc, cl, ix, cn)
+        return (bx, sc, cl, ix, cn) if bx is not None else packed
 
     def last_levels(self) -> List[torch.Tensor]:
         """Copies of the engine-owned logits written by the last detect() (one [B,A,S,S,5+C] tensor per level)."""

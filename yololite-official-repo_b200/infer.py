@@ -139,10 +139,11 @@ class YoloLite:
         return results
 
     def predict_batch(self, images_u8: torch.Tensor, conf: float = 0.4, iou: float = 0.5, max_det: int = 300, img_size: int = 0,
-                      cap: Optional[int] = None):
+                      cap: Optional[int] = None, packed: Optional[torch.Tensor] = None):
         """Batched device-side predict: uint8 [B,H,W,3] BGR (CUDA) -> Detections (fixed capacity, letterboxed coordinates)
         + the letterbox geometry.  No host synchronisation; call `.to_list()` / `backmap` on the result when needed.  The
-        Detections alias buffers owned by this object: valid until the next predict_batch call with the same shape."""
+        Detections alias buffers owned by this object: valid until the next predict_batch call with the same shape.
+        packed: optional [B, cap+1, 6] tensor the kernel fills as well (the multi-GPU gather payload, dist.gather_packed)."""
         from .post import Detections
         S = int(img_size) if img_size else self.img_size
         B, h0, w0 = images_u8.shape[0], images_u8.shape[1], images_u8.shape[2]
@@ -165,7 +166,7 @@ class YoloLite:
                           torch.zeros((B,), device=dev, dtype=torch.int32))
             self._obuf_key = okey
         # forward + postprocess as ONE C call (one CUDA graph launch once the engine has captured it)
-        bx, sc, cl, ix, cn = self.model.detect(x, S, conf, iou, max_det, cap, outputs=self._obuf)
+        bx, sc, cl, ix, cn = self.model.detect(x, S, conf, iou, max_det, cap, outputs=self._obuf, packed=packed)
         return Detections(bx, sc, cl, ix, cn), geo
 
     def to_json(self, result: dict) -> dict:

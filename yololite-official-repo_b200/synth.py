@@ -27,6 +27,15 @@ MODEL_YAMLS = {   # configs/models/*.yaml
 }
 
 
+# configs/models/yololite_*.yaml: YOLOLiteMS (dense 3x3 + SiLU FPN) over tf_efficientnet_lite*; only their FPN + heads are lowered
+# (engine from_features=True).  FEATURE_CHANNELS: channels of the [c2, c3, c4, c5] taps of those timm backbones.
+MODEL_YAMLS.update({
+    "yololite_n": dict(arch="YOLOLiteMS", backbone="tf_efficientnet_lite0", depth_multiple=1.0, width_multiple=1.0, fpn_channels=196, head_depth=1),
+    "yololite_m": dict(arch="YOLOLiteMS", backbone="tf_efficientnet_lite2", depth_multiple=1.0, width_multiple=1.0, fpn_channels=328, head_depth=2),
+})
+FEATURE_CHANNELS = {"tf_efficientnet_lite0": (24, 40, 112, 320), "tf_efficientnet_lite2": (24, 48, 120, 352)}
+
+
 def make_meta(model: str = "edge_n", num_classes: int = 80, img_size: int = 640, use_p2: bool = False,
               use_p6: bool = False, anchors: int = 1) -> dict:
     m = dict(MODEL_YAMLS[model])
@@ -38,8 +47,9 @@ def make_meta(model: str = "edge_n", num_classes: int = 80, img_size: int = 640,
             "config": {"model": m, "training": {"img_size": img_size, "use_p6": use_p6, "use_p2": use_p2}}}
 
 
-def state_shapes(meta: dict) -> "OrderedDict[str, tuple]":
-    cfg = packer.parse_meta(meta)
+def state_shapes(meta: dict, feat_chs=None) -> "OrderedDict[str, tuple]":
+    """feat_chs: channels of the backbone taps when only the FPN + heads are wanted (no backbone keys)."""
+    cfg = packer.parse_meta(meta, from_features=feat_chs is not None)
     out: "OrderedDict[str, tuple]" = OrderedDict()
 
     def bn(p, c):
@@ -47,32 +57,35 @@ def state_shapes(meta: dict) -> "OrderedDict[str, tuple]":
             out[f"{p}.{k}"] = (c,)
         out[f"{p}.num_batches_tracked"] = ()
 
-    table, mult, stem = packer.BACKBONES[cfg.backbone]
-    out["backbone.conv_stem.weight"] = (stem, 3, 3, 3)
-    bn("backbone.bn1", stem)
-    cin = stem
-    feats = [stem]
-    for si, stage in enumerate(table):
-        for bi, spec in enumerate(stage):
-            key = f"backbone.blocks.{si}.{bi}"
-            if spec[0] == "cn":
-                _, k, s, c = spec
-                cout = packer._round_ch(c * mult)
-                out[key + ".conv.weight"] = (cout, cin, k, k)
-                bn(key + ".bn1", cout)
-            else:
-                _, ks, km, s, e, c = spec
-                cout, mid = packer._round_ch(c * mult), packer._round_ch(cin * e)
-                if ks:
-                    out[key + ".dw_start.conv.weight"] = (cin, 1, ks, ks); bn(key + ".dw_start.bn", cin)
-                out[key + ".pw_exp.conv.weight"] = (mid, cin, 1, 1); bn(key + ".pw_exp.bn", mid)
-                if km:
-                    out[key + ".dw_mid.conv.weight"] = (mid, 1, km, km); bn(key + ".dw_mid.bn", mid)
-                out[key + ".pw_proj.conv.weight"] = (cout, mid, 1, 1); bn(key + ".pw_proj.bn", cout)
-            cin = cout
-            nxt = table[si + 1][0] if si + 1 < len(table) else None
-            if bi == len(stage) - 1 and (nxt is None or (nxt[2] if nxt[0] == "cn" else nxt[3]) > 1):
-                feats.append(cout)
+    if feat_chs is not None:
+        feats = list(feat_chs)
+    else:
+        table, mult, stem = packer.BACKBONES[cfg.backbone]
+        out["backbone.conv_stem.weight"] = (stem, 3, 3, 3)
+        bn("backbone.bn1", stem)
+        cin = stem
+        feats = [stem]
+        for si, stage in enumerate(table):
+            for bi, spec in enumerate(stage):
+                key = f"backbone.blocks.{si}.{bi}"
+                if spec[0] == "cn":
+                    _, k, s, c = spec
+                    cout = packer._round_ch(c * mult)
+                    out[key + ".conv.weight"] = (cout, cin, k, k)
+                    bn(key + ".bn1", cout)
+                else:
+                    _, ks, km, s, e, c = spec
+                    cout, mid = packer._round_ch(c * mult), packer._round_ch(cin * e)
+                    if ks:
+                        out[key + ".dw_start.conv.weight"] = (cin, 1, ks, ks); bn(key + ".dw_start.bn", cin)
+                    out[key + ".pw_exp.conv.weight"] = (mid, cin, 1, 1); bn(key + ".pw_exp.bn", mid)
+                    if km:
+                        out[key + ".dw_mid.conv.weight"] = (mid, 1, km, km); bn(key + ".dw_mid.bn", mid)
+                    out[key + ".pw_proj.conv.weight"] = (cout, mid, 1, 1); bn(key + ".pw_proj.bn", cout)
+                cin = cout
+                nxt = table[si + 1][0] if si + 1 < len(table) else None
+                if bi == len(stage) - 1 and (nxt is None or (nxt[2] if nxt[0] == "cn" else nxt[3]) > 1):
+                    feats.append(cout)
     chs = feats[-(4 if cfg.use_p2 else 3):]
     Fc, d, C = cfg.fpn_channels, cfg.depth, cfg.num_classes
     cpu = cfg.arch == "yololitems_cpu"
@@ -107,11 +120,11 @@ def state_shapes(meta: dict) -> "OrderedDict[str, tuple]":
     return out
 
 
-def random_checkpoint(meta: dict, seed: int = 0, obj_bias: Optional[float] = None, head_std: float = 0.1) -> dict:
+def random_checkpoint(meta: dict, seed: int = 0, obj_bias: Optional[float] = None, head_std: float = 0.1, feat_chs=None) -> dict:
     g = torch.Generator().manual_seed(seed)
-    C = packer.parse_meta(meta).num_classes
+    C = packer.parse_meta(meta, from_features=feat_chs is not None).num_classes
     sd: Dict[str, torch.Tensor] = OrderedDict()
-    for k, shp in state_shapes(meta).items():
+    for k, shp in state_shapes(meta, feat_chs).items():
         if k.endswith("num_batches_tracked"):
             sd[k] = torch.tensor(0, dtype=torch.long)
         elif k.endswith(("running_mean",)) or (k.endswith(".bias") and len(shp) == 1 and ".out." not in k):
