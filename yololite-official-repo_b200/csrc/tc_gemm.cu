@@ -244,13 +244,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   }
   for (int i = threadIdx.x; i < 128; i += blockDim.x) bias_s[i] = (c.bias && i < p.Nc && chunk_n0 + i < c.Cout) ? __ldg(c.bias + chunk_n0 + i) : 0.f;
   if (MODE == 2) {
-    const int cp = p.nslab * 32;
-    for (int i = threadIdx.x; i < (KS * KS + 1) * cp; i += TC_THREADS) {
-      const int tap = i / cp, k = i - tap * cp;
-      float v = 0.f;
-      if (k < p.K) v = tap < KS * KS ? __ldg(c.w2 + tap * c.Cin + k) : (c.b2 ? __ldg(c.b2 + k) : 0.f);
-      w2s[i] = v;
+    // depthwise taps + bias row, 16 B at a time (Cin % 4 == 0; w2 / b2 are 16 B aligned blob arrays)
+    const int cp4 = p.nslab * 8, k4n = c.Cin >> 2;
+    for (int i = threadIdx.x; i < (KS * KS + 1) * cp4; i += TC_THREADS) {
+      const int tap = i / cp4, k4 = i - tap * cp4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k4 < k4n) {
+        if (tap < KS * KS) v = __ldg(reinterpret_cast<const float4*>(c.w2 + (size_t)tap * c.Cin) + k4);
+        else if (c.b2) v = __ldg(reinterpret_cast<const float4*>(c.b2) + k4);
+      }
+      reinterpret_cast<float4*>(w2s)[i] = v;
     }
+  }
+  if (warp == TC_TMA_WARP && lane == 0) {          // descriptor fetches off the critical path of the first loads / stores
+    if (MODE == 2 || p.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
