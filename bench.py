@@ -324,6 +324,7 @@ def setup_dist():
         # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # whatever NCCL prints goes to stderr
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=c.dev)
         c.dist = dist

@@ -83,6 +83,10 @@ typedef struct yl_op {
   int32_t act2;      /* YL_OP_DWPW: yl_act applied to the depthwise result before the pointwise conv;
                         YL_OP_STEM2: yl_act of the fused pointwise conv */
   int32_t stride2;   /* YL_OP_DWPW: stride of the depthwise stage (0 or 1 = 1, 2); the output size follows it */
+  int32_t wt_layout; /* K axis of the wt_off image: 0 = k = (ky*k + kx)*cin + ci packed densely (slabs of 32 may straddle taps);
+                        1 = every tap padded to a multiple of 32 channels, k' = (ky*k + kx)*ceil32(cin) + ci (dense k x k convs with
+                        stride 1 and a long cin: each K-slab is then ONE shifted TMA box of the NHWC input, no gather) */
+  int32_t reserved0;
 } yl_op;
 
 /* Build an engine on `device` from a layer program and a HOST weight blob.

@@ -28,7 +28,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_op_struct_layout_matches_header():
     from yololite_b200 import _lib as L
-    assert ctypes.sizeof(L.YlOp) == 12 * 4 + 6 * 8 + 2 * 4
+    assert ctypes.sizeof(L.YlOp) == 12 * 4 + 6 * 8 + 4 * 4
+    assert L.YlOp.wt_layout.offset == 104
     assert L.YlOp.b2_off.offset == 88 and L.YlOp.act2.offset == 96
     assert L.YlOp.w_off.offset == 48
 

@@ -13,7 +13,7 @@ TOL = 2e-4
 
 
 def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, w2=None, use_tc=1, nchw_input=False,
-         b2=None, act2=0, stride2=0):
+         b2=None, act2=0, stride2=0, tap_layout=False):
     """w: [Cout,Cin,k,k] torch fp32 (dense) or [C,1,k,k] (depthwise); returns NHWC output (or head layout)."""
     from yololite_b200 import _lib as L, packer
     lib = L.lib()
@@ -45,7 +45,11 @@ def _run(kind, x_nhwc, w, bias, k, stride, act=0, res=None, up=None, anchors=0, 
         op.cin, op.cout = w.shape[1], cout
         wm = packer._gemm_w(wn)
         op.w_off = add(wm)
-        op.wt_off = add(packer.tc_image(wm, cout))
+        if tap_layout:      # per-tap padded K axis (yl_op.wt_layout = 1): the TMA-fed dense conv path
+            op.wt_off = add(packer.tc_image(packer.tap_padded(wm, k * k, w.shape[1]), cout))
+            op.wt_layout = 1
+        else:
+            op.wt_off = add(packer.tc_image(wm, cout))
         if kind == L.OP_DWPW:
             op.k, op.k2 = 1, int(w2.shape[-1])
             op.w2_off = add(np.transpose(w2.double().numpy(), (2, 3, 1, 0)).reshape(op.k2 * op.k2, -1))
@@ -279,3 +283,22 @@ def test_fused_stem_conv(hw, n2, bf16x3, pw):
     L.check(L.lib().yl_run_op(ctypes.byref(op), dblob.data_ptr(), xc.data_ptr(), None, None, out.data_ptr(), B, hw[0], hw[1], 0, 0, 1, None))
     torch.cuda.synchronize()
     assert float((out.cpu() - want).abs().max()) <= TOL
+
+
+@pytest.mark.parametrize("cin,cout,h,w,act,res", [(96, 96, 20, 20, 2, False), (196, 196, 13, 11, 2, False), (328, 328, 16, 24, 2, False),
+                                                   (72, 40, 9, 33, 1, True), (128, 256, 8, 16, 0, False)])
+def test_dense3x3_tma_tap_path(cin, cout, h, w, act, res):
+    """Dense 3x3 stride-1 conv with a long Cin (the YOLOLiteMS FPN smoothing convs, model_v2.py:15-22,201-203): every K-slab of the A
+    operand is ONE TMA box of the NHWC input shifted by the tap (zero-filled outside = the padding); weights resident or streamed."""
+    from yololite_b200 import _lib as L
+    g = torch.Generator().manual_seed(cin + cout + h)
+    x = torch.randn(2, h, w, cin, generator=g)
+    wt = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    b = torch.randn(cout, generator=g)
+    r = torch.randn(2, h, w, cout, generator=g) if res else None
+    n0 = L.lib().yl_stat(b"tc_launches")
+    got = _run(1, x, wt, b, 3, 1, act, res=r, use_tc=2, tap_layout=True)
+    assert L.lib().yl_stat(b"tc_launches") == n0 + 1
+    want = _ref(x.permute(0, 3, 1, 2), wt, b, 3, 1, act, res=r)
+    assert got.shape == want.shape
+    assert float((got - want).abs().max()) <= TOL

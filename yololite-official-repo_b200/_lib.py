@@ -13,7 +13,8 @@ class YlOp(ctypes.Structure):
                 ("stride", ctypes.c_int32), ("act", ctypes.c_int32), ("anchors", ctypes.c_int32),
                 ("k2", ctypes.c_int32), ("w_off", ctypes.c_int64), ("b_off", ctypes.c_int64),
                 ("w2_off", ctypes.c_int64), ("wt_off", ctypes.c_int64), ("w3_off", ctypes.c_int64),
-                ("b2_off", ctypes.c_int64), ("act2", ctypes.c_int32), ("stride2", ctypes.c_int32)]
+                ("b2_off", ctypes.c_int64), ("act2", ctypes.c_int32), ("stride2", ctypes.c_int32),
+                ("wt_layout", ctypes.c_int32), ("reserved0", ctypes.c_int32)]
 
     def __init__(self, *args, **kw):
         super().__init__(*args, **kw)

@@ -72,6 +72,7 @@ struct ConvParams {
   int act;
   int act2;                          // DWPW: activation between the depthwise and the pointwise stage
   int anchors;                       // >0: head layout [B,A,H,W,D], D = Cout/anchors
+  int wt_layout;                     // yl_op.wt_layout of the tcgen05 weight image (1: every tap padded to 32 channels)
 };
 
 // TMA descriptor over an fp32 tensor (tc_gemm.cu): dims / box innermost first, strides in bytes for dims 1..rank-1;

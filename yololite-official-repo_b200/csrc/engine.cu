@@ -137,6 +137,7 @@ static void fill_params(ConvParams& p, const yl_op& op, const float* blob, const
   p.KS = op.k; p.stride = op.stride; p.pad = op.k / 2;
   p.Hu = hu; p.Wu = wu;
   p.act = op.act; p.anchors = op.anchors;
+  p.wt_layout = op.wt_layout;
   if (op.kind == YL_OP_DWPW) {                                        // geometry / epilogue of the depthwise stage
     p.KS = op.k2; p.pad = op.k2 / 2; p.stride = op.stride2 > 1 ? op.stride2 : 1;
     p.b2 = op.b2_off >= 0 ? blob + op.b2_off : nullptr;
@@ -153,7 +154,11 @@ static void fill_params(ConvParams& p, const yl_op& op, const float* blob, const
 static int tc_mode_for(const yl_op& op, const ConvParams& p, int use_tc, int hout, int wout) {
   if (!(use_tc && op.wt_off >= 0 && (op.kind == YL_OP_CONV || op.kind == YL_OP_DWPW))) return -1;
   const int mode = op.kind == YL_OP_DWPW ? 2 : (op.k == 1 && op.stride == 1) ? 0 : 1;
-  const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * op.cin;
+  const int K = (mode == 0 || mode == 2) ? op.cin : op.k * op.k * (op.wt_layout == 1 ? (op.cin + 31) / 32 * 32 : op.cin);
+  // the per-tap padded image only exists for the TMA path of dense stride-1 convs; anything else with that layout runs on SIMT
+  if (op.wt_layout == 1 && !(mode == 1 && op.stride == 1 && !p.up && op.anchors <= 1 && (op.cout & 3) == 0 &&
+                             (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0))
+    return -1;
   // small layers (K or N < 32) are per-tile-overhead bound on the tensor-core pipeline and already stream at ~2 TB/s on the
   // SIMT kernel: keep them there unless the caller forces the tensor path (use_tc == 2).  Rows of N % 4 != 0 floats are not
   // 16-byte aligned: the tensor-core epilogues read residual / upsample sources with 16-byte loads, so that (unused by the
@@ -546,6 +551,7 @@ int yl_engine_create(const yl_op* ops, int32_t n_ops, const float* blob_host, si
     YL_REQUIRE(op.w_off >= 0 && (size_t)op.w_off < blob_floats, "w_off out of range");
     YL_REQUIRE(op.b_off < (int64_t)blob_floats, "b_off out of range");
     YL_REQUIRE((op.w_off & 3) == 0 && (op.b_off < 0 || (op.b_off & 3) == 0), "blob offsets must be 16-byte aligned");
+    YL_REQUIRE(op.wt_layout == 0 || (op.wt_layout == 1 && op.kind == YL_OP_CONV && op.k > 1 && op.stride == 1), "wt_layout 1: dense k x k stride-1 convs");
     if (op.src <= YL_SRC_FEATURE(0)) {
       YL_REQUIRE(YL_FEATURE_INDEX(op.src) < MAX_FEATS && op.kind == YL_OP_CONV, "feature inputs: at most 8, read by YL_OP_CONV ops");
       n_feats = std::max(n_feats, YL_FEATURE_INDEX(op.src) + 1);

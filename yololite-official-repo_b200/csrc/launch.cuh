@@ -64,6 +64,9 @@ struct TcParams {
   int stg_stride;       // bytes of epilogue staging per warp (TC_STG_BYTES; the smem-starved MODE 3 packs them at 4608)
   int tma_out;          // epilogue writes each warp's 32 x 32 block through a swizzled staging tile + TMA tensor store
   int tma_a;            // MODE 0: the A tile (128 rows x 32 k, SWIZZLE_128B) is loaded by TMA; producers only derive lo
+  int tap_tma;          // MODE 1, stride 1, per-tap padded weight image: every K-slab of A is one TMA box of the NHWC input (32 channels
+                        // x tile_w x tile_h pixels, shifted by the tap, zero-filled outside = the padding); spt = slabs per tap
+  int spt;
   int wstream;          // MODE 2: the weight image does not fit next to the halo ring: each K-slab of W (hi, lo) is
                         // streamed from L2 into the A stage's own W slot with cp.async.bulk
   int dense_epi;       // 1: epilogue stages whole [32][N] warp slabs in smem and writes them as one aligned span

@@ -199,6 +199,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   float* dense_stage = bias_s + 128;                               // dense epilogue only: 4 warps x 32 x Nc floats
 
   const int chunk_n0 = blockIdx.y * p.Nc;          // first output channel of this CTA's N-chunk
+  // streamed weights: rows of this chunk that exist in the image (a partial last chunk leaves stale rows in its slot: they only
+  // feed output columns >= Cout, which are never stored)
+  const uint32_t w_rows_bytes = (uint32_t)min(p.Nc, p.Npad - chunk_n0) * 64u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     }
   }
   if (warp == TC_TMA_WARP && lane == 0) {          // descriptor fetches off the critical path of the first loads / stores
-    if (MODE == 2 || p.tma_a) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    if (MODE == 2 || p.tma_a || p.tap_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -279,7 +282,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
     const int ch = t & 7, r0 = t >> 3;
-    if (MODE == 0 && p.tma_a) {
+    if ((MODE == 0 && p.tma_a) || (MODE == 1 && p.tap_tma)) {
+      // (MODE 1 with per-tap TMA boxes: the same, the 128 rows are the tile's pixels)
       // The TMA warp lands each K-slab of the fp32 A tile (128 rows x 128 B, SWIZZLE_128B) in the stage's a1|a2 area; every producer
       // thread reads its own 16 B pieces (4 with 8 producer warps, 8 with 4), and -- a warp covers whole rows, so a __syncwarp
       // separates all reads of a row from the writes -- overwrites the rows IN PLACE with the bf16 splits a1 | a2 (a3 goes to
@@ -568,7 +572,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 7u);          // the MMAs that read this stage are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
-                       "r"((uint32_t)TC_P12_BYTES + (p.wstream ? w_slab_bytes : 0u)) : "memory");
+                       "r"((uint32_t)TC_P12_BYTES + (p.wstream ? 3u * w_rows_bytes : 0u)) : "memory");
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                        ::"r"(smem_u32(a_ring) + (uint32_t)stage * (uint32_t)TC_STAGE_BYTES), "l"(&tmap), "r"(s * 32), "r"(tile * TC_BM), "r"(bar)
                        : "memory");
@@ -577,7 +581,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             for (int q3 = 0; q3 < 3; ++q3)
               asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                            ::"r"(smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes),
-                             "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_split_bytes), "r"(bar) : "memory");
+                             "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_rows_bytes), "r"(bar) : "memory");
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -602,6 +606,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             : "memory");
         if (++slot == p.halo_slots) { slot = 0; hphase ^= 1; }
       }
+    } else if (p.tap_tma && lane == 0) {
+      // dense k x k, stride 1: K-slab s = tap * spt + cs is the box of 32 channels [32 cs, 32 cs + 32) x tile_w x tile_h pixels of the
+      // NHWC input shifted by the tap (ky - pad, kx - pad); pixels outside the image and channels past Cin arrive as zeros.  It lands
+      // as 128 rows of 128 B (SWIZZLE_128B) = the layout the producers convert in place.  Streamed weights ride on the same barrier.
+      const int per_img = p.tiles_x * p.tiles_y;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int b = tile / per_img, rem = tile - b * per_img;
+        const int y0 = (rem / p.tiles_x) * p.tile_h - c.pad, x0 = (rem % p.tiles_x) * p.tile_w - c.pad;
+        int tap = 0, cs = 0;
+        for (int s = 0; s < p.nslab; ++s) {
+          const int ky = tap / c.KS, kx = tap - ky * c.KS;
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 18u);          // the MMAs that read this stage are done
+          const uint32_t bar = smem_u32(&wfull_bar[stage]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar),
+                       "r"((uint32_t)TC_P12_BYTES + (p.wstream ? 3u * w_rows_bytes : 0u)) : "memory");
+          asm volatile(
+              "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+              ::"r"(smem_u32(a_ring) + (uint32_t)stage * (uint32_t)TC_STAGE_BYTES), "l"(&tmap), "r"(cs * 32), "r"(x0 + kx), "r"(y0 + ky), "r"(b), "r"(bar)
+              : "memory");
+          if (p.wstream) {
+#pragma unroll
+            for (int q3 = 0; q3 < 3; ++q3)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                           ::"r"(smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes),
+                             "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_rows_bytes), "r"(bar) : "memory");
+          }
+          if (++cs == p.spt) { cs = 0; ++tap; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
     } else if (p.wstream && lane == 0) {
       // generic gather (cp.async producers) with a K too long for resident weights (the dense 3x3 convs of the YOLOLiteMS FPN,
       // K = 9 * 196 ... 9 * 328): this thread streams the K-slab of W (three splits) that belongs to each A stage from L2
@@ -612,12 +648,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 9u);          // the MMAs that read this stage's W slot are done
           const uint32_t bar = smem_u32(&wfull_bar[stage]);
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_slab_bytes) : "memory");
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3u * w_rows_bytes) : "memory");
 #pragma unroll
           for (int q3 = 0; q3 < 3; ++q3)
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(w_base) + (uint32_t)stage * w_slab_bytes + (uint32_t)q3 * w_split_bytes),
-                           "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_split_bytes), "r"(bar) : "memory");
+                           "l"(p.wimg + (((size_t)s * 3 + q3) * p.Npad + chunk_n0) * 16), "r"(w_rows_bytes), "r"(bar) : "memory");
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     }
@@ -696,7 +732,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           if (p.wstream) {
             // this stage's W slab: MODES 1 / 2 wait for it here; in MODE 0 it shares the A tile's barrier, which the
             // producers have already waited on
-            if (MODE == 2 || MODE == 1) mbar_wait(smem_u32(&wfull_bar[stage]), phase, p.dbg, 15u);
+            if (MODE == 2 || (MODE == 1 && !p.tap_tma)) mbar_wait(smem_u32(&wfull_bar[stage]), phase, p.dbg, 15u);
             b1 = smem_u32(w_base) + (uint32_t)stage * w_slab_bytes;
           }
           const uint32_t b2 = b1 + w_split_bytes, b3 = b2 + w_split_bytes;
@@ -741,7 +777,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     const int tile_step = p.epi2 ? 2 * (int)gridDim.x : (int)gridDim.x;
     for (int tile = blockIdx.x + (p.epi2 ? grp * (int)gridDim.x : 0); tile < tiles; tile += tile_step) {
       const int mw = tile * TC_BM + q * 32;                   // first row of this warp (linear modes)
-      const bool spatial = MODE == 2 || (MODE == 1 && p.tma_a);   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
+      const bool spatial = MODE == 2 || (MODE == 1 && (p.tma_a || p.tap_tma));   // tile = tile_h x tile_w output pixels (else 128 consecutive rows)
       const int rows_ok = spatial ? 32 : min(32, M - mw);      // rows of this warp inside the matrix
       if (p.tma_out) {
         // TMEM -> registers (lane = row) -> +bias, act -> SWIZZLE_128B staging tile (conflict-free 16 B stores) -> ONE TMA tensor
@@ -1048,9 +1084,8 @@ static bool tc_plan_stream(int nslab, int Npad, size_t dw_bytes, TcPlan* pl) {
 static bool tc_plan_stream0(int N, int anchors, int max_chunks, TcPlan* pl) {
   const int Npad = (N + 15) / 16 * 16;
   for (int nch = 1; nch < max_chunks; ++nch) {        // only if it needs fewer N chunks than the resident plan
-    if ((Npad / 16) % nch) continue;
-    const int Nc = Npad / nch;
-    if (Nc > 128) continue;
+    const int Nc = ((Npad / 16 + nch - 1) / nch) * 16;      // the last chunk may be partial: its missing rows are never copied
+    if (Nc > 128 || (nch - 1) * Nc >= Npad) continue;
     const size_t dense_bytes = tc_dense_epi(N, anchors, Nc, nch) ? (size_t)4 * 32 * Nc * 4 : 0;
     const size_t fixed = TC_AUX_BYTES + dense_bytes + 1024;
     const size_t per_stage = (size_t)TC_STAGE_BYTES + (size_t)3 * Nc * 64;
@@ -1186,7 +1221,12 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   p.mode = mode;
   p.dbg = debug_words();
   YL_REQUIRE(mode >= 0 && mode <= 2, "tcgen05 conv modes: 0 pointwise, 1 dense KxK, 2 depthwise -> pointwise");
-  p.K = (mode == 0 || mode == 2) ? c.Cin : c.KS * c.KS * c.Cin;
+  const bool tap = mode == 1 && c.wt_layout == 1;          // per-tap padded K axis: dense k x k stride-1 conv fed by shifted TMA boxes
+  p.spt = tap ? (c.Cin + 31) / 32 : 0;
+  p.K = (mode == 0 || mode == 2) ? c.Cin : tap ? c.KS * c.KS * p.spt * 32 : c.KS * c.KS * c.Cin;
+  YL_REQUIRE(c.wt_layout == 0 || (tap && c.stride == 1 && c.pad == c.KS / 2 && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0 &&
+                                  (reinterpret_cast<uintptr_t>(c.in) & 15) == 0),
+             "per-tap padded weight image: dense k x k stride-1 conv on a 16-byte aligned input");
   p.nslab = (p.K + 31) / 32;
   p.Npad = (c.Cout + 15) / 16 * 16;
   TcPlan pl;
@@ -1212,7 +1252,15 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   p.num_tiles = (int)((p.M + TC_BM - 1) / TC_BM);
   // MODE 1 with a small Cin: whole-Cin halo tiles by TMA + shared-memory im2col (see the producer branch)
   size_t smem_override = 0;
-  if (mode == 1 && tma_env && pl.nchunks == 1 && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (c.Cin & 3) == 0 && c.Cin <= 64 &&
+  if (tap) {
+    p.tap_tma = 1;
+    p.tile_w = TC_TILE_W; p.tile_h = TC_TILE_H;
+    p.tiles_x = (c.Wout + p.tile_w - 1) / p.tile_w;
+    p.tiles_y = (c.Hout + p.tile_h - 1) / p.tile_h;
+    p.num_tiles = c.B * p.tiles_x * p.tiles_y;
+    p.dense_epi = 0;
+  }
+  if (!tap && mode == 1 && tma_env && pl.nchunks == 1 && !c.up && c.anchors <= 1 && (c.Cout & 3) == 0 && (c.Cin & 3) == 0 && c.Cin <= 64 &&
       (c.stride == 1 || c.stride == 2) && c.pad == c.KS / 2 && (reinterpret_cast<uintptr_t>(c.in) & 15) == 0) {
     const int tw = TC_TILE_W, th = TC_TILE_H;
     const int hw_ = (tw - 1) * c.stride + c.KS, hh_ = (th - 1) * c.stride + c.KS;
@@ -1273,6 +1321,12 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
     if (int rc = make_a_tmap(&tmap, c.in, p.M, c.Cin)) return rc;
     p.tma_a = 1;
   }
+  if (tap) {
+    const unsigned long long dims[4] = {(unsigned long long)c.Cin, (unsigned long long)c.Win, (unsigned long long)c.Hin, (unsigned long long)c.B};
+    const unsigned long long strides[3] = {(unsigned long long)c.Cin * 4, (unsigned long long)c.Win * c.Cin * 4, (unsigned long long)c.Hin * c.Win * c.Cin * 4};
+    const unsigned int box[4] = {32, (unsigned)p.tile_w, (unsigned)p.tile_h, 1};
+    if (int rc = make_tmap_f32(&tmap, c.in, 4, dims, strides, box, true)) return rc;
+  }
   if (mode == 1 && p.tma_a) {
     const unsigned long long dims[4] = {(unsigned long long)c.Cin, (unsigned long long)c.Win, (unsigned long long)c.Hin, (unsigned long long)c.B};
     const unsigned long long strides[3] = {(unsigned long long)c.Cin * 4, (unsigned long long)c.Win * c.Cin * 4, (unsigned long long)c.Hin * c.Win * c.Cin * 4};
@@ -1288,7 +1342,7 @@ int tc_prepare(const ConvParams& c, const float* wimg, int mode, int sm_count, T
   CUtensorMap& omap = L->omap;
   memset(&omap, 0, sizeof(omap));
   static const int tmaout_env = [] { const char* e = getenv("YL_TC_TMAOUT"); return e ? atoi(e) : 1; }();
-  const bool spatial = mode == 2 || (mode == 1 && p.tma_a);
+  const bool spatial = mode == 2 || (mode == 1 && (p.tma_a || p.tap_tma));
   if (tmaout_env && !p.dense_epi && (c.Cout & 3) == 0 && c.anchors <= 1 && !c.res && (!c.up || (mode == 0 && (reinterpret_cast<uintptr_t>(c.up) & 15) == 0)) && c.Cout >= 32 &&
       (p.nchunks == 1 || (p.Nc & 31) == 0) && (reinterpret_cast<uintptr_t>(c.out) & 15) == 0 && (!spatial || 32 % p.tile_w == 0)) {
     int rc;

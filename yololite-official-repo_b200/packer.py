@@ -217,6 +217,16 @@ def tc_image(wm: np.ndarray, n_out: int) -> np.ndarray:
     return out.reshape(-1).view(np.float32)
 
 
+def tap_padded(wm: np.ndarray, taps: int, cin: int) -> np.ndarray:
+    """[taps*cin][N] GEMM matrix -> [taps*ceil32(cin)][N] with every tap's channel block zero-padded to a multiple of 32
+    (yl_op.wt_layout = 1): a K-slab of 32 then never straddles two taps."""
+    cp = (cin + 31) // 32 * 32
+    out = np.zeros((taps * cp, wm.shape[1]), np.float64)
+    for t in range(taps):
+        out[t * cp:t * cp + cin] = wm[t * cin:(t + 1) * cin]
+    return out
+
+
 def stem_u8_matrix(ws: np.ndarray, b0: np.ndarray) -> np.ndarray:
     """Stem weights for uint8 input as a float64 [32 out][32 k] matrix.  ws: [27][32] (k = (ky*3+kx)*3 + ci, BN folded),
     b0: [32].  Columns 0..26 multiply the raw pixel bytes (channel ci of the RGB tensor), 27 a constant 1, 28 / 29 / 30
@@ -288,13 +298,20 @@ def lower(state_dict: dict, meta: dict, fuse_dwpw: bool = True, reuse_buffers: b
     def emit(kind, src: Optional[_T], cout, red, k=1, stride=1, act=L.ACT_NONE, w=None, b=None, res: Optional[_T] = None,
              up: Optional[_T] = None, anchors=0, level=None, w2=None, k2=0, w3=None, b2=None, act2=L.ACT_NONE, stride2=0) -> Optional[_T]:
         dst = None if level is not None else P.new(cout, red)
+        cin_ = 3 if src is None else src.C
+        # dense k x k, stride 1, long cin (the 3x3 convs of the YOLOLiteMS FPN): per-tap padded K axis -> every K-slab is one TMA box
+        tap_layout = bool(tensor_cores and kind == L.OP_CONV and k > 1 and stride == 1 and cin_ > 64 and cin_ % 4 == 0)
+        wmat = np.asarray(w, np.float64).reshape(-1, w.shape[-1])
+        if tap_layout:
+            wmat = tap_padded(wmat, k * k, cin_)
         P.ops.append(dict(kind=kind, src=(-1 if src is None else src.vid), dst=(-(1 + level) if level is not None else dst.vid),
                           res=(-1 if res is None else res.vid), up=(-1 if up is None else up.vid),
                           cin=(3 if src is None else src.C), cout=cout, k=k, stride=stride, act=act, anchors=anchors, k2=k2,
                           w_off=P.add_blob(w), b_off=(-1 if b is None else P.add_blob(_pad4(b))),
                           w2_off=(-1 if w2 is None else P.add_blob(w2)), w3_off=(-1 if w3 is None else P.add_blob(w3)),
                           b2_off=(-1 if b2 is None else P.add_blob(_pad4(b2))), act2=act2, stride2=stride2,
-                          wt_off=(P.add_blob(tc_image(np.asarray(w, np.float64).reshape(-1, w.shape[-1]), cout))
+                          wt_layout=(1 if tap_layout else 0),
+                          wt_off=(P.add_blob(tc_image(wmat, cout))
                                   if tensor_cores and kind in (L.OP_CONV, L.OP_DWPW, L.OP_STEM2) and cout >= 8 and w.shape[0] >= 8 else -1)))
         return dst
 
@@ -513,7 +530,7 @@ def to_c(P: Program):
     for i, op in enumerate(P.ops):
         o = arr[i]
         for f in ("kind", "src", "dst", "res", "up", "cin", "cout", "k", "stride", "act", "anchors", "k2", "w_off", "b_off",
-                  "w2_off", "wt_off", "w3_off", "b2_off", "act2", "stride2"):
+                  "w2_off", "wt_off", "w3_off", "b2_off", "act2", "stride2", "wt_layout"):
             setattr(o, f, int(op[f]))
     blob = np.concatenate(P.blob).astype(np.float32, copy=False)
     assert blob.size == P.blob_len
