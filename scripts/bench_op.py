@@ -18,7 +18,7 @@ from yololite_b200 import _lib as L, packer  # noqa: E402
 KINDS = {"stem": 0, "conv": 1, "dw": 2, "dwpw": 3, "stem2": 4}
 
 
-def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0, stride2=0):
+def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0, stride2=0, tap=0):
     g = np.random.RandomState(0)
     blob, off = [], [0]
 
@@ -55,7 +55,10 @@ def build(kind, cin, cout, k, stride, act, up, res, k2=3, act2=0, stride2=0):
         wm = np.zeros((kk * kk * cin, (cout + 3) // 4 * 4))
         wm[:, :cout] = g.randn(kk * kk * cin, cout) / np.sqrt(kk * kk * cin)
         op.w_off = add(wm)
-        op.wt_off = add(packer.tc_image(wm, cout))
+        if tap:
+            op.wt_off = add(packer.tc_image(packer.tap_padded(wm, kk * kk, cin), cout)); op.wt_layout = 1
+        else:
+            op.wt_off = add(packer.tc_image(wm, cout))
         if kind == "dwpw":
             op.k, op.k2, op.act2, op.stride2 = 1, k2, act2, stride2
             op.w2_off = add(g.randn(k2 * k2, cin) / k2)
@@ -81,9 +84,10 @@ def main():
     ap.add_argument("--act2", type=int, default=0)
     ap.add_argument("--stride2", type=int, default=0)
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--tap", type=int, default=0, help="per-tap padded weight image (TMA-fed dense conv)")
     a = ap.parse_args()
     lib = L.lib()
-    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res, a.k2, a.act2, a.stride2)
+    op, blob = build(a.kind, a.cin, a.cout, a.k, a.stride, a.act, a.up, a.res, a.k2, a.act2, a.stride2, a.tap)
     B, H = a.batch, a.hw
     k = op.k
     ho = (H + 2 * (k // 2) - k) // a.stride + 1
@@ -111,7 +115,8 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.iters
     nbytes = 4 * (x.numel() + out.numel() + (res.numel() if res is not None else 0) + (up.numel() if up is not None else 0))
-    print(json.dumps({"kind": a.kind, "cin": a.cin, "cout": a.cout, "k": a.k, "stride": a.stride, "hw": H, "B": B, "tc": a.tc,
+    macs = B * ho * ho * a.cout * a.cin * a.k * a.k if a.kind == "conv" else 0
+    print(json.dumps({"TFLOPs_useful": 2 * macs / ms / 1e9, "kind": a.kind, "cin": a.cin, "cout": a.cout, "k": a.k, "stride": a.stride, "hw": H, "B": B, "tc": a.tc,
                       "up": a.up, "res": a.res, "k2": a.k2, "ms": ms, "GBps": nbytes / ms / 1e6}))
 
 
