@@ -9,9 +9,11 @@
 // accumulator blocks [main | corr | corr]: the kernel is bound by shared-memory operand reads, and this halves them.
 //
 // Per 16x8 tile of conv2 output pixels (one persistent CTA per SM, 17 warps, warp-specialised):
-//   warps 8-15  producers: cp.async the 3 x 67 x 36 fp32 input patch (NCHW) into shared memory, build the stem's im2col
-//               operand (K = 27 taps + a constant-1 column that carries the folded BN bias, padded to 32) for five
-//               128-row tiles covering the 33 x 17 halo of stem output pixels;
+//   warps 8-15  producers, two groups of 4 warps that take alternate stem sub-tiles: the 3 x 67 x 36 fp32 input patch (NCHW)
+//               arrives as one TMA box; every thread builds ONE whole row of the stem's im2col operand (K = 27 taps + a
+//               constant-1 column that carries the folded BN bias, padded to 32; all patch offsets are immediates) for
+//               five 128-row tiles covering the 33 x 17 halo of stem output pixels.  The rows are in PLANE order (row q
+//               = pixel q of the parity planes below), so the epilogue's plane stores are bank-conflict free;
 //   warp  16    one thread issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128, N = 96|64|32, K = 32) into a ring of
 //               three TMEM accumulator triples, GEMM2 = conv2 as nine per-tap GEMMs (M = 128, N = 3|2|1 x N2, K = 32);
 //   warps 0-7   epilogue: TMEM -> ReLU -> bf16 triple -> shared-memory halo stored as four parity planes
@@ -50,6 +52,15 @@ constexpr int S2_ACC1_RING = 3;                            // stem accumulator r
 constexpr uint32_t S2_ACC1_COLS = 96, S2_ACC2_COL = S2_ACC1_RING * S2_ACC1_COLS, S2_ACC2_COLS = 96;   // conv2: 2 x 3*N2 (<= 96)
 // parity planes (py, px): pixel offsets inside one split, pitch 9 (px = 0) or 8 (px = 1)
 __host__ __device__ constexpr int s2_plane_off(int py, int px) { return py ? (px ? 433 : 289) : (px ? 153 : 0); }
+constexpr int S2_ROWS = S2_MT * 128;                       // rows of the five stem GEMM tiles (561 real)
+// GEMM1 row q (= pixel index inside the parity planes) -> halo pixel, packed hy | hx << 8 (0xFFFF: padding row)
+__host__ __device__ inline unsigned s2_row_pixel(int q) {
+  if (q >= S2_HPIX) return 0xFFFFu;
+  const int py = q >= 289, px = py ? q >= 433 : q >= 153;
+  const int l = q - s2_plane_off(py, px), pitch = px ? 8 : 9;
+  const int i = l / pitch, jx = l - i * pitch;
+  return (unsigned)(2 * i + py) | ((unsigned)(2 * jx + px) << 8);
+}
 
 
 namespace s2 {
@@ -115,6 +126,17 @@ __device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t&
   h = __floats2bfloat162_rn(a, b);
   p3 = *reinterpret_cast<uint32_t*>(&h);
 }
+// the same for relu(a), relu(b): round-toward-zero splits keep every residual's sign, so the .relu of the conversion is the
+// ReLU (a negative input yields 0 | 0 | 0); x = x1 + x2 + x3 exactly (8 + 8 + 8 significand bits)
+__device__ __forceinline__ void split3_relu(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
+  a -= __uint_as_float(p1 << 16);
+  b -= __uint_as_float(p1 & 0xFFFF0000u);
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
+  a -= __uint_as_float(p2 << 16);
+  b -= __uint_as_float(p2 & 0xFFFF0000u);
+  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
+}
 }  // namespace s2
 
 template <int A1S>      // stem operand stages (2; 1 when the 32-channel conv2 weights leave no room for two)
@@ -143,10 +165,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
   uint64_t* patch_full = bars + 21;    //      TMA complete_tx -> producers: the input patch of the next tile has landed
   float* pws = reinterpret_cast<float*>(bars + 24);       // fused pointwise: 16 x 16 weights + 16 biases
+  unsigned short* lut = reinterpret_cast<unsigned short*>(pws + 16 * 16 + 16);   // [S2_ROWS] row -> halo pixel (s2_row_pixel)
   const bool has_pw = p.pw != nullptr;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS); mbar_init(smem_u32(&a1_empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS / 2); mbar_init(smem_u32(&a1_empty[s]), 1); }
     for (int j = 0; j < S2_ACC1_RING; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
     mbar_init(smem_u32(patch_full), 1);
     mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
@@ -167,6 +190,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   }
   if (has_pw)
     for (int i = threadIdx.x; i < 16 * 16 + 16; i += S2_THREADS) pws[i] = __ldg(p.pw + i);
+  for (int i = threadIdx.x; i < S2_ROWS; i += S2_THREADS) lut[i] = (unsigned short)s2_row_pixel(i);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -181,14 +205,11 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
 
   if (warp >= S2_EPI_WARPS && warp < S2_EPI_WARPS + S2_PROD_WARPS) {
     // =============================== producers ===============================
+    // Two groups of 4 warps take alternate stem sub-tiles n (group = n & 1 = the A1 stage when there are two); inside a group
+    // every thread builds ONE whole im2col row: its 27 patch offsets are immediates, the row's 4 x 16 B chunks x 3 splits are
+    // twelve conflict-free 16 B stores.
     const int t = threadIdx.x - 32 * S2_EPI_WARPS;          // 0..255
-    const int ch = t & 3, r0 = t >> 2;                      // 16 B chunk (8 k's) of rows r0 and r0 + 64
-    int poff[8];                                            // patch offsets of this thread's 8 k's; -1: constant 1, -2: zero
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int k = ch * 8 + m, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-      poff[m] = k < 27 ? (ci * S2_PR + ky) * S2_PP + kx + 1 : (k == 27 ? -1 : -2);
-    }
+    const int grp = t >> 7, r = t & 127;
     // the 3 x 67 x 36 input patch (NCHW, zero outside the image = the stem's padding) is ONE TMA box over [B*3][H][W]
     auto issue_patch = [&](int tile) {
       if (p.in_u8) {
@@ -224,19 +245,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     };
     issue_patch(blockIdx.x);
     uint32_t pphase = 0;
-    uint32_t n = 0;                                          // running stem-tile counter -> A1 stage / phase
-    // image mode: byte offsets of the 8 k's of a chunk (BGR bytes: channel ci of the RGB tensor is byte 2 - ci); the patch row
-    // starts 4 bytes before pixel ixa.  k = 27: constant 1 (bias + full mean/std term), 28: top-border row, 29: left-border
-    // column, 30: top-left corner (they take back the padded taps' share of the mean/std term), 31: zero
-    // image mode uses a warp-uniform chunk (so that only the warps of chunk 3 handle the constant / border columns):
-    // chunk = warp & 3, rows (lane + 32 * (t >> 7)) and + 64
-    const int ch8 = (t >> 5) & 3, rb8 = (t & 31) + 32 * (t >> 7);
-    int boff8[8];
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-      const int k = ch8 * 8 + m, tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
-      boff8[m] = k < 27 ? ky * S2_U8_PITCH + 4 + (kx + 1) * 3 + (2 - ci) : 0;
-    }
+    uint32_t n = 0;                                          // running stem-tile counter -> group, A1 stage, phases
+    const uint32_t rsw = (uint32_t)(r >> 1) & 3u, rbase = (uint32_t)r * 64u;      // this row's line and SWIZZLE_64B XOR
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
       if (p.in_u8) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -248,51 +258,70 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
       const int trem = tile % per_img;
       const int sy0 = 2 * S2_TH * (trem / p.tiles_x) - 1, sx0 = 2 * S2_TW * (trem % p.tiles_x) - 1;   // stem-output coords of halo (0,0)
       for (int j = 0; j < S2_MT; ++j, ++n) {
-        const uint32_t stage = A1S == 2 ? (n & 1u) : 0u, aph = A1S == 2 ? ((n >> 1) & 1u) : (n & 1u);
-        mbar_wait(smem_u32(&a1_empty[stage]), aph ^ 1u);
-        unsigned char* st = a1 + stage * S2_A1_STAGE;
+        if ((int)(n & 1u) != grp) continue;
+        const uint32_t stage = A1S == 2 ? (uint32_t)grp : 0u;
+        const uint32_t px = lut[j * 128 + r];
+        const bool live = px != 0xFFFFu;                      // rows past the 561 halo pixels are never read back
+        const int hy = (int)(px & 0xFFu), hx = (int)(px >> 8);
+        uint4 o1[4], o2[4], o3[4];
         if (p.in_u8) {
+          // image mode: BGR bytes (channel ci of the RGB tensor is byte 2 - ci), the patch row starts 4 bytes before pixel ixa.
+          // k = 27: constant 1 (bias + full mean/std term), 28: top-border row, 29: left-border column, 30: top-left corner
+          // (they take back the padded taps' share of the mean/std term), 31: zero.  Integers 0..255 are exact in ONE bf16.
+          if (live) {
+            const unsigned char* pb = reinterpret_cast<const unsigned char*>(patch) + 2 * hy * S2_U8_PITCH + 6 * hx;
+            float e[32];
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int r = rb8 + 64 * i, q = j * 128 + r;
-            if (q < S2_HPIX) {
-              const int hy = q / S2_HW, hx = q - hy * S2_HW;
-              const unsigned char* pb = reinterpret_cast<const unsigned char*>(patch) + 2 * hy * S2_U8_PITCH + 6 * hx;
-              float e[8];
+            for (int k = 0; k < 27; ++k) {
+              const int tap = k / 3, ci = k - tap * 3, ky = tap / 3, kx = tap - ky * 3;
+              e[k] = (float)pb[ky * S2_U8_PITCH + 4 + (kx + 1) * 3 + (2 - ci)];
+            }
+            const float top = (sy0 + hy == 0) ? 1.f : 0.f, left = (sx0 + hx == 0) ? 1.f : 0.f;
+            e[27] = 1.f; e[28] = top; e[29] = left; e[30] = top * left; e[31] = 0.f;
 #pragma unroll
-              for (int m = 0; m < 8; ++m) e[m] = (float)pb[boff8[m]];
-              if (ch8 == 3) {                                  // k = 24..26 are taps; 27: 1, 28: top row, 29: left column, 30: corner
-                const float top = (sy0 + hy == 0) ? 1.f : 0.f, left = (sx0 + hx == 0) ? 1.f : 0.f;
-                e[3] = 1.f; e[4] = top; e[5] = left; e[6] = top * left; e[7] = 0.f;
-              }
-              uint4 o1;                                       // integers 0..255 are exact in bf16
-              __nv_bfloat162 h;
-              h = __floats2bfloat162_rn(e[0], e[1]); o1.x = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(e[2], e[3]); o1.y = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(e[4], e[5]); o1.z = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2bfloat162_rn(e[6], e[7]); o1.w = *reinterpret_cast<uint32_t*>(&h);
-              *reinterpret_cast<uint4*>(st + (uint32_t)r * 64u + (uint32_t)((ch8 ^ ((r >> 1) & 3)) << 4)) = o1;
+            for (int c = 0; c < 4; ++c) {
+              uint32_t w[4];
+#pragma unroll
+              for (int m = 0; m < 4; ++m)      // exact: pack the high halves of the two fp32 patterns
+                w[m] = __byte_perm(__float_as_uint(e[8 * c + 2 * m]), __float_as_uint(e[8 * c + 2 * m + 1]), 0x7632);
+              o1[c] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
-        } else
+        } else if (live) {
+          const float* pb = patch + 2 * hy * S2_PP + 2 * hx;
+          float e[32];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int r = r0 + 64 * i, q = j * 128 + r;
-          if (q < S2_HPIX) {
-            const int hy = q / S2_HW, hx = q - hy * S2_HW;
-            const float* pb = patch + 2 * hy * S2_PP + 2 * hx;
-            float e[8];
+          for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-            for (int m = 0; m < 8; ++m) e[m] = poff[m] >= 0 ? pb[poff[m]] : (poff[m] == -1 ? 1.f : 0.f);
-            uint4 o1, o2, o3;
-            split3(e[0], e[1], o1.x, o2.x, o3.x);
-            split3(e[2], e[3], o1.y, o2.y, o3.y);
-            split3(e[4], e[5], o1.z, o2.z, o3.z);
-            split3(e[6], e[7], o1.w, o2.w, o3.w);
-            const uint32_t off = (uint32_t)r * 64u + (uint32_t)((ch ^ ((r >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4*>(st + off) = o1;
-            *reinterpret_cast<uint4*>(st + S2_A1_SPLIT + off) = o2;
-            *reinterpret_cast<uint4*>(st + 2 * S2_A1_SPLIT + off) = o3;
+            for (int ky = 0; ky < 3; ++ky) {
+              // taps kx = 0, 1, 2 are patch columns 2 hx + 1 .. + 3: one 4 B and one (8 B aligned) 8 B load
+              const float* q = pb + (ci * S2_PR + ky) * S2_PP;
+              const float e0 = q[1];
+              const float2 e12 = *reinterpret_cast<const float2*>(q + 2);
+              e[(ky * 3 + 0) * 3 + ci] = e0; e[(ky * 3 + 1) * 3 + ci] = e12.x; e[(ky * 3 + 2) * 3 + ci] = e12.y;
+            }
+          e[27] = 1.f; e[28] = 0.f; e[29] = 0.f; e[30] = 0.f; e[31] = 0.f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            split3(e[8 * c + 0], e[8 * c + 1], o1[c].x, o2[c].x, o3[c].x);
+            split3(e[8 * c + 2], e[8 * c + 3], o1[c].y, o2[c].y, o3[c].y);
+            split3(e[8 * c + 4], e[8 * c + 5], o1[c].z, o2[c].z, o3[c].z);
+            split3(e[8 * c + 6], e[8 * c + 7], o1[c].w, o2[c].w, o3[c].w);
+          }
+        }
+        // the MMAs that read this stage (sub-tile n - A1S) are done; their commits alternate between the two barriers, so a
+        // group never waits on a barrier whose phase the OTHER group's sub-tile could have advanced (no parity aliasing)
+        if (n >= (uint32_t)A1S) mbar_wait(smem_u32(&a1_empty[(n - A1S) & 1u]), ((n - A1S) >> 1) & 1u);
+        if (live) {
+          unsigned char* st = a1 + stage * S2_A1_STAGE + rbase;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (((uint32_t)c ^ rsw) << 4);
+            *reinterpret_cast<uint4*>(st + off) = o1[c];
+            if (!p.in_u8) {
+              *reinterpret_cast<uint4*>(st + S2_A1_SPLIT + off) = o2[c];
+              *reinterpret_cast<uint4*>(st + 2 * S2_A1_SPLIT + off) = o3[c];
+            }
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -331,7 +360,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
               mma_bf16(d0 + 64u, da0 + (uint64_t)((2 * S2_A1_SPLIT + ks * 32) >> 4), db, i1c, 1u);    // A3 x [W1]
             }
           }
-          mma_commit(smem_u32(&a1_empty[stage]));
+          mma_commit(smem_u32(&a1_empty[n & 1u]));        // the barriers alternate with n even when there is one stage (see producers)
           mma_commit(smem_u32(&acc1_full[slot]));
           if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
         }
@@ -376,7 +405,6 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     // =============================== epilogue ===============================
     const int q4 = warp & 3, half = warp >> 2;                 // TMEM lane quarter, column half
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    const uint32_t pl_u = smem_u32(planes);
     auto out_epi = [&](uint32_t it, int tile) {
       const uint32_t b = it & 1u;
       if (has_pw) {
@@ -468,52 +496,51 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
       const int rem = tile % per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int sy0 = 2 * S2_TH * ty - 1, sx0 = 2 * S2_TW * tx - 1;
+      // only tiles on the image border have halo pixels outside the stem output (conv2's zero padding)
+      const bool border = sy0 < 0 || sx0 < 0 || sy0 + S2_HH > p.Hs || sx0 + S2_HW > p.Ws;
       for (int j = 0; j < S2_MT; ++j) {
         mbar_wait(smem_u32(&acc1_full[slot]), sphase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         float v[16];                                          // main + corr + corr of this thread's 16 channels
         {
           const uint32_t ta = lane_addr + S2_ACC1_COLS * slot + 16u * (uint32_t)half;
+          uint32_t m[16], k[16], k2[16];
+          tmem_ld16(ta, m);
+          tmem_ld16(ta + 32u, k);
+          tmem_ld16(ta + 64u, k2);
+          tmem_ld_wait();
 #pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            uint32_t m[8], k[8], k2[8];
-            tmem_ld8(ta + 8u * h8, m);
-            tmem_ld8(ta + 32u + 8u * h8, k);
-            tmem_ld8(ta + 64u + 8u * h8, k2);
-            tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) v[8 * h8 + c] = __uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c]));
-          }
+          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c]));
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc1_free[slot]));
         if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
         if (j == 0) mbar_wait(smem_u32(halo_free), (it & 1u) ^ 1u);   // conv2 of the previous tile has read the halo
-        const int q = j * 128 + q4 * 32 + lane;
-        if (q < S2_HPIX) {
-          const int hy = q / S2_HW, hx = q - hy * S2_HW;
-          const int sy = sy0 + hy, sx = sx0 + hx;
-          const bool in_img = sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws;      // outside = conv2's zero padding
+        // GEMM1 row q IS pixel q of the parity planes (s2_row_pixel): consecutive lanes write consecutive 64 B plane rows, whose
+        // SWIZZLE_64B chunk positions make every 8-lane group of a 16 B store hit eight different bank groups
+        const uint32_t q = (uint32_t)(j * 128 + q4 * 32 + lane);
+        if (q < (uint32_t)S2_HPIX) {
+          if (border) {
+            const uint32_t pxl = lut[q];
+            const int sy = sy0 + (int)(pxl & 0xFFu), sx = sx0 + (int)(pxl >> 8);
+            if (!(sy >= 0 && sy < p.Hs && sx >= 0 && sx < p.Ws)) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) v[c] = 0.f;
+            }
+          }
           uint32_t o1[8], o2[8], o3[8];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float a = fmaxf(v[2 * c], 0.f);          // bias rides in the GEMM (k = 27)
-            float b = fmaxf(v[2 * c + 1], 0.f);
-            if (!in_img) { a = 0.f; b = 0.f; }
-            split3(a, b, o1[c], o2[c], o3[c]);
-          }
-          const int py = hy & 1, px = hx & 1;
-          const uint32_t pix = (uint32_t)s2_plane_off(py, px) + (uint32_t)(hy >> 1) * (px ? 8u : 9u) + (uint32_t)(hx >> 1);
-          const uint32_t row = pl_u + pix * 64u;
-          const uint32_t sw = (row >> 7) & 3u;
-          const uint32_t d0 = (row - pl_u) + ((((uint32_t)(2 * half)) ^ sw) << 4), d1 = (row - pl_u) + ((((uint32_t)(2 * half + 1)) ^ sw) << 4);
-          *reinterpret_cast<uint4*>(planes + d0) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-          *reinterpret_cast<uint4*>(planes + d1) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
-          *reinterpret_cast<uint4*>(planes + S2_PLANE_BYTES + d0) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-          *reinterpret_cast<uint4*>(planes + S2_PLANE_BYTES + d1) = make_uint4(o2[4], o2[5], o2[6], o2[7]);
-          *reinterpret_cast<uint4*>(planes + 2 * S2_PLANE_BYTES + d0) = make_uint4(o3[0], o3[1], o3[2], o3[3]);
-          *reinterpret_cast<uint4*>(planes + 2 * S2_PLANE_BYTES + d1) = make_uint4(o3[4], o3[5], o3[6], o3[7]);
+          for (int c = 0; c < 8; ++c) split3_relu(v[2 * c], v[2 * c + 1], o1[c], o2[c], o3[c]);   // ReLU; the bias rode in the GEMM (k = 27)
+          const uint32_t sw = (q >> 1) & 3u;                   // planes is 1024 B aligned: the XOR is address bits 7-8 = (q >> 1) & 3
+          unsigned char* row = planes + q * 64u;
+          const uint32_t d0 = (((uint32_t)(2 * half)) ^ sw) << 4, d1 = (((uint32_t)(2 * half + 1)) ^ sw) << 4;
+          *reinterpret_cast<uint4*>(row + d0) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+          *reinterpret_cast<uint4*>(row + d1) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+          *reinterpret_cast<uint4*>(row + S2_PLANE_BYTES + d0) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+          *reinterpret_cast<uint4*>(row + S2_PLANE_BYTES + d1) = make_uint4(o2[4], o2[5], o2[6], o2[7]);
+          *reinterpret_cast<uint4*>(row + 2 * S2_PLANE_BYTES + d0) = make_uint4(o3[0], o3[1], o3[2], o3[3]);
+          *reinterpret_cast<uint4*>(row + 2 * S2_PLANE_BYTES + d1) = make_uint4(o3[4], o3[5], o3[6], o3[7]);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -537,7 +564,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
 // ---- host side -----------------------------------------------------------------------------------
 static size_t stem2_smem_bytes(int N2, int a1_stages) {
   return (size_t)27 * N2 * 64 + S2_WST_BYTES + (size_t)a1_stages * S2_A1_STAGE + 3 * S2_PLANE_BYTES + S2_PATCH_BYTES + 256 +
-         (16 * 16 + 16) * 4 + 1024;
+         (16 * 16 + 16) * 4 + S2_ROWS * 2 + 1024;
 }
 static int stem2_a1_stages(int N2) { return stem2_smem_bytes(N2, 2) <= (size_t)227 * 1024 ? 2 : 1; }
 

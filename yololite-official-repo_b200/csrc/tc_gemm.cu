@@ -282,6 +282,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // 256 threads; per K-slab each thread owns 4 x 16 B of the A tile: rows (t>>3)+32*i, chunk t&7.
     const int t = threadIdx.x;                      // 0..255
     const int ch = t & 7, r0 = t >> 3;
+    // Row owned by this thread in piece `ip` of a K-slab for the TMA-fed paths: each 8-lane group of a warp covers one whole row
+    // (8 x 16 B); the two rows of a HALF-warp differ in bits 0 and 2 (pairs 0/5, 2/7, 1/4, 3/6 of an 8-row group), so their a1 | a2
+    // halves of the SWIZZLE_128B lines and their 64 B lines of the third plane fall into different banks (the plain t >> 3 order put
+    // rows r, r + 1 of a half-warp on the same 16 banks: every 8 B split store took two wavefronts).
+    const int l3 = lane >> 3, rsel = (l3 & 2) + 5 * (l3 & 1);
+    auto piece_row = [&](int ip) { return 8 * (warp + p.prod_warps * (ip >> 1)) + (rsel ^ (ip & 1)); };
     if ((MODE == 0 && p.tma_a) || (MODE == 1 && p.tap_tma)) {
       // (MODE 1 with per-tap TMA boxes: the same, the 128 rows are the tile's pixels)
       // The TMA warp lands each K-slab of the fp32 A tile (128 rows x 128 B, SWIZZLE_128B) in the stage's a1|a2 area; every producer
@@ -290,8 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       // the stage's second plane).
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
-      const int rstep = p.prod_warps * 4;                         // rows covered by one pass of the producer threads
-      const int npass = TC_BM / (4 * rstep);                     // passes of 4 pieces per thread: 1 or 2
+      const int npass = TC_BM / (16 * p.prod_warps);             // passes of 4 pieces per thread: 1 (8 producer warps) or 2 (4)
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < total; ++j) {
@@ -301,12 +306,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           float4 a[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int row = r0 + rstep * (4 * ps + i);
+            const int row = piece_row(4 * ps + i);
             a[i] = *reinterpret_cast<const float4*>(st + (uint32_t)(row >> 3) * 1024u + (uint32_t)(row & 7) * 128u + (uint32_t)((ch ^ (row & 7)) << 4));
           }
           __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 4; ++i) store_split3(st, r0 + rstep * (4 * ps + i), ch, a[i]);
+          for (int i = 0; i < 4; ++i) store_split3(st, piece_row(4 * ps + i), ch, a[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       int hp0[4];                                     // halo pixel of tap (0,0) for this thread's 4 output rows
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int row = r0 + 32 * i;
+        const int row = piece_row(i);
         hp0[i] = (row / p.tile_w) * c.stride * HW + (row % p.tile_w) * c.stride;
       }
       int stage = 0, slot = 0;
@@ -343,7 +348,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1, p.dbg, 3u);
           unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) store_split3(st, r0 + 32 * i, ch, a[i]);
+          for (int i = 0; i < 4; ++i) store_split3(st, piece_row(i), ch, a[i]);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
