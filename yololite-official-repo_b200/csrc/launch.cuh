@@ -18,6 +18,16 @@ namespace yl {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// One lane of a CONVERGED warp.  Guarding the single-thread roles (tcgen05.mma / TMA issue) with elect.sync instead of `lane == 0`
+// tells ptxas that exactly one thread is active: the UTCHMMA / UTMALDG operands then live in uniform registers and the instructions
+// issue back to back.  With `lane == 0` every one of them sat in a PLOP3 / ELECT / BRA.U.ANY "waterfall" loop (~7 dependent
+// instructions per MMA), and the issuing thread of the stem kernel was busy 93 % of the time -- it was the bottleneck.
+__device__ __forceinline__ bool elect_one() {
+  unsigned pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_ex(void (*kern)(KArgs...), dim3 grid, int threads, size_t smem, cudaStream_t st, int pdl, Args&&... args) {
   cudaLaunchConfig_t cfg = {};

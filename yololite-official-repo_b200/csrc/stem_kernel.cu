@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     }
   } else if (warp == S2_MMA_WARP) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       auto idesc = [](uint32_t N) { return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((128u >> 4) << 24); };
       const uint32_t i1a = idesc(96), i1b = idesc(64), i1c = idesc(32);
       const uint32_t N2 = (uint32_t)p.N2, i2a = idesc(3 * N2), i2b = idesc(2 * N2), i2c = idesc(N2);

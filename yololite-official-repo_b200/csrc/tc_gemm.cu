@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       reinterpret_cast<float4*>(w2s)[i] = v;
     }
   }
-  if (warp == TC_TMA_WARP && lane == 0) {          // descriptor fetches off the critical path of the first loads / stores
+  if (warp == TC_TMA_WARP && elect_one()) {          // descriptor fetches off the critical path of the first loads / stores
     if (MODE == 2 || p.tma_a || p.tap_tma) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     if (p.tma_out) asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
   }
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     }
   } else if (MODE == 0 && warp == TC_TMA_WARP) {
     // =============================== TMA issuer (MODE 0) ===============================
-    if (p.tma_a && lane == 0) {
+    if (p.tma_a && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -595,7 +595,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     __syncwarp();
   } else if (MODE == 1 && warp == TC_TMA_WARP) {
     // =============================== TMA issuer (MODE 1: whole-Cin halo per tile) ===============================
-    if (p.tma_a && lane == 0) {
+    const bool leader = elect_one();        // ONE election for the whole role: a second elect.sync further down the else-if chain
+                                            // would wait forever for the lane that took an earlier branch
+    if (p.tma_a && leader) {
       const int per_img = p.tiles_x * p.tiles_y;
       int slot = 0;
       uint32_t hphase = 0;
@@ -611,7 +613,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
             : "memory");
         if (++slot == p.halo_slots) { slot = 0; hphase ^= 1; }
       }
-    } else if (p.tap_tma && lane == 0) {
+    } else if (p.tap_tma && leader) {
       // dense k x k, stride 1: K-slab s = tap * spt + cs is the box of 32 channels [32 cs, 32 cs + 32) x tile_w x tile_h pixels of the
       // NHWC input shifted by the tap (ky - pad, kx - pad); pixels outside the image and channels past Cin arrive as zeros.  It lands
       // as 128 rows of 128 B (SWIZZLE_128B) = the layout the producers convert in place.  Streamed weights ride on the same barrier.
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
-    } else if (p.wstream && lane == 0) {
+    } else if (p.wstream && leader) {
       // generic gather (cp.async producers) with a K too long for resident weights (the dense 3x3 convs of the YOLOLiteMS FPN,
       // K = 9 * 196 ... 9 * 328): this thread streams the K-slab of W (three splits) that belongs to each A stage from L2
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     __syncwarp();
   } else if (MODE == 2 && warp == TC_TMA_WARP) {
     // =============================== TMA issuer (MODE 2) ===============================
-    if (lane == 0) {
+    if (elect_one()) {
       const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = my_tiles * p.nslab;
       const int per_img = p.tiles_x * p.tiles_y;
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // Two accumulators per tile: `main` takes A1*W1 (16-bit products: most of them add to the accumulator without loss), `corr`
     // the five 2^-8 ... 2^-16 smaller cross terms.  The tensor core truncates its fp32 accumulator, so the chain that carries the
     // magnitude must be short and made of short products; the epilogue adds the two in fp32 (round to nearest).
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc_n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.Nc >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint32_t idesc_2n = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * p.Nc) >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0;
