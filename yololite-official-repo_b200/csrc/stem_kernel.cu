@@ -288,18 +288,30 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
             }
           }
         } else if (live) {
-          const float* pb = patch + 2 * hy * S2_PP + 2 * hx;
+          // taps kx = 0, 1, 2 are patch columns 2 hx + 1 .. + 3.  Rows come in plane order, so consecutive lanes step hx by 2 = one
+          // 16 B group of the patch row: even hx takes .y .z .w of ONE conflict-free 16 B load, odd hx .w of that group and the
+          // first 8 B of the next (a 4 B load per tap would be a 4-way bank conflict at this 16 B lane stride)
+          const float* pb = patch + 2 * hy * S2_PP + 4 * (hx >> 1);
           float e[32];
+          if (hx & 1) {
 #pragma unroll
-          for (int ci = 0; ci < 3; ++ci)
+            for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky) {
-              // taps kx = 0, 1, 2 are patch columns 2 hx + 1 .. + 3: one 4 B and one (8 B aligned) 8 B load
-              const float* q = pb + (ci * S2_PR + ky) * S2_PP;
-              const float e0 = q[1];
-              const float2 e12 = *reinterpret_cast<const float2*>(q + 2);
-              e[(ky * 3 + 0) * 3 + ci] = e0; e[(ky * 3 + 1) * 3 + ci] = e12.x; e[(ky * 3 + 2) * 3 + ci] = e12.y;
-            }
+              for (int ky = 0; ky < 3; ++ky) {
+                const float* q = pb + (ci * S2_PR + ky) * S2_PP;
+                const float4 a = *reinterpret_cast<const float4*>(q);
+                const float2 b = *reinterpret_cast<const float2*>(q + 4);
+                e[(ky * 3 + 0) * 3 + ci] = a.w; e[(ky * 3 + 1) * 3 + ci] = b.x; e[(ky * 3 + 2) * 3 + ci] = b.y;
+              }
+          } else {
+#pragma unroll
+            for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+              for (int ky = 0; ky < 3; ++ky) {
+                const float4 a = *reinterpret_cast<const float4*>(pb + (ci * S2_PR + ky) * S2_PP);
+                e[(ky * 3 + 0) * 3 + ci] = a.y; e[(ky * 3 + 1) * 3 + ci] = a.z; e[(ky * 3 + 2) * 3 + ci] = a.w;
+              }
+          }
           e[27] = 1.f; e[28] = 0.f; e[29] = 0.f; e[30] = 0.f; e[31] = 0.f;
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
