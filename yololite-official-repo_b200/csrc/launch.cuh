@@ -2,6 +2,7 @@
 // computed ONCE per (op, shape, pointers) by *_prepare and replayed by *_launch, so yl_forward does no planning, no
 // cuTensorMapEncodeTiled and no allocation per call.  Also: programmatic dependent launch (PDL) helpers.
 #pragma once
+#include <cstdint>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -17,6 +18,34 @@ namespace yl {
 // data only) overlaps the previous kernel's tail.  Without the attribute both instructions are no-ops.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ---- packed fp32 pairs (sm_100: FFMA2 / FADD2, two IEEE fp32 operations per issue slot; results identical to the scalar ones).
+// The 64-bit values are register pairs: packing / unpacking compiles to no instruction when the pair is already adjacent
+// (e.g. the halves of a 16-byte shared-memory load).
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// two fp32 -> packed bf16 pair (element 0 in the low half) for each of the three splits: x = x1 + x2 + x3 up to 2^-24 |x|.
+// RELU: round-toward-zero splits keep every residual's sign, so the .relu of the conversion IS the ReLU (a negative input yields
+// 0 | 0 | 0) and x = x1 + x2 + x3 exactly.  The residuals x - x1 are one FFMA2 (x1 * -1 + x, exact) per pair.
+template <bool RELU>
+__device__ __forceinline__ void split3_pair(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  const f32x2 neg1 = pack2(-1.f, -1.f);
+  f32x2 ab = pack2(a, b);
+  if (RELU) asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
+  ab = fma2(pack2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xFFFF0000u)), neg1, ab);
+  unpack2(ab, a, b);
+  if (RELU) asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
+  ab = fma2(pack2(__uint_as_float(p2 << 16), __uint_as_float(p2 & 0xFFFF0000u)), neg1, ab);
+  unpack2(ab, a, b);
+  if (RELU) asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
+}
 
 // One lane of a CONVERGED warp.  Guarding the single-thread roles (tcgen05.mma / TMA issue) with elect.sync instead of `lane == 0`
 // tells ptxas that exactly one thread is active: the UTCHMMA / UTMALDG operands then live in uniform registers and the instructions

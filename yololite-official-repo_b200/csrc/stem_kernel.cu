@@ -113,30 +113,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// two fp32 -> packed bf16 pair (element 0 in the low half) for each of the three splits
-__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  p1 = *reinterpret_cast<uint32_t*>(&h);
-  a -= __uint_as_float(p1 << 16);
-  b -= __uint_as_float(p1 & 0xFFFF0000u);
-  h = __floats2bfloat162_rn(a, b);
-  p2 = *reinterpret_cast<uint32_t*>(&h);
-  a -= __uint_as_float(p2 << 16);
-  b -= __uint_as_float(p2 & 0xFFFF0000u);
-  h = __floats2bfloat162_rn(a, b);
-  p3 = *reinterpret_cast<uint32_t*>(&h);
-}
-// the same for relu(a), relu(b): round-toward-zero splits keep every residual's sign, so the .relu of the conversion is the
-// ReLU (a negative input yields 0 | 0 | 0); x = x1 + x2 + x3 exactly (8 + 8 + 8 significand bits)
-__device__ __forceinline__ void split3_relu(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
-  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
-  a -= __uint_as_float(p1 << 16);
-  b -= __uint_as_float(p1 & 0xFFFF0000u);
-  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
-  a -= __uint_as_float(p2 << 16);
-  b -= __uint_as_float(p2 & 0xFFFF0000u);
-  asm("cvt.rz.relu.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
-}
+__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) { split3_pair<false>(a, b, p1, p2, p3); }
+__device__ __forceinline__ void split3_relu(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) { split3_pair<true>(a, b, p1, p2, p3); }
 }  // namespace s2
 
 template <int A1S>      // stem operand stages (2; 1 when the 32-channel conv2 weights leave no room for two)
@@ -445,16 +423,22 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
             xin[c] = act_fn(__uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c])) + __ldg(p.bias2 + c), p.act);
         }
         float yo[16];
+        {
+          f32x2 y2[8];                                          // packed pairs (FFMA2)
 #pragma unroll
-        for (int n = 0; n < 16; ++n) yo[n] = pws[256 + n];
+          for (int n = 0; n < 8; ++n) y2[n] = pack2(pws[256 + 2 * n], pws[256 + 2 * n + 1]);
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
+          for (int kk = 0; kk < 16; ++kk) {
+            const f32x2 xk = pack2(xin[kk], xin[kk]);
 #pragma unroll
-          for (int n4 = 0; n4 < 4; ++n4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(pws + kk * 16 + n4 * 4);      // same address in every lane: broadcast
-            yo[4 * n4 + 0] = fmaf(xin[kk], w4.x, yo[4 * n4 + 0]); yo[4 * n4 + 1] = fmaf(xin[kk], w4.y, yo[4 * n4 + 1]);
-            yo[4 * n4 + 2] = fmaf(xin[kk], w4.z, yo[4 * n4 + 2]); yo[4 * n4 + 3] = fmaf(xin[kk], w4.w, yo[4 * n4 + 3]);
+            for (int n4 = 0; n4 < 4; ++n4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(pws + kk * 16 + n4 * 4);      // same address in every lane: broadcast
+              y2[2 * n4] = fma2(xk, pack2(w4.x, w4.y), y2[2 * n4]);
+              y2[2 * n4 + 1] = fma2(xk, pack2(w4.z, w4.w), y2[2 * n4 + 1]);
+            }
           }
+#pragma unroll
+          for (int n = 0; n < 8; ++n) unpack2(y2[n], yo[2 * n], yo[2 * n + 1]);
         }
         if (y < p.Ho && x < p.Wo) {
           float* dst = p.out + (((size_t)bi * p.Ho + y) * p.Wo + x) * 16;
@@ -522,7 +506,10 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
           tmem_ld16(ta + 64u, k2);
           tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 16; ++c) v[c] = __uint_as_float(m[c]) + (__uint_as_float(k[c]) + __uint_as_float(k2[c]));
+          for (int c = 0; c < 16; c += 2)      // main + (corr + corr), as packed pairs (FADD2)
+            unpack2(add2(pack2(__uint_as_float(m[c]), __uint_as_float(m[c + 1])),
+                         add2(pack2(__uint_as_float(k[c]), __uint_as_float(k[c + 1])), pack2(__uint_as_float(k2[c]), __uint_as_float(k2[c + 1])))),
+                    v[c], v[c + 1]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();

@@ -131,16 +131,7 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t* r) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// two fp32 -> packed bf16 pair (element 0 in the low half) for each of the three splits: x = x1 + x2 + x3 up to 2^-24 |x|
-__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(b), "f"(a));
-  a -= __uint_as_float(p1 << 16);
-  b -= __uint_as_float(p1 & 0xFFFF0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(b), "f"(a));
-  a -= __uint_as_float(p2 << 16);
-  b -= __uint_as_float(p2 & 0xFFFF0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(b), "f"(a));
-}
+__device__ __forceinline__ void split3(float a, float b, uint32_t& p1, uint32_t& p2, uint32_t& p3) { split3_pair<false>(a, b, p1, p2, p3); }
 
 // Write the three bf16 splits of 4 consecutive k (16 B fp32 source chunk `c` = k 4c..4c+3 of the K-slab) of A row `row` into a stage:
 //   a1 -> bytes [0,64) of the row's 128 B SWIZZLE_128B line, a2 -> bytes [64,128), a3 -> the row's 64 B SWIZZLE_64B line of the P3 plane.
@@ -485,62 +476,83 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           if (valid2) {
             const unsigned char* hb = halo + (size_t)c_slot * p.halo_bytes + hoff2;
             const float* wk = w2s + c_s * 32 + ch * 4;
+            // the multiply-adds run as packed pairs (FFMA2: channels (0,1) and (2,3) of every 16-byte piece)
+            f32x2 acc[4][2];
             {
               const float4 b4 = *reinterpret_cast<const float4*>(wk + KS * KS * cp);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) a[i] = b4;
+              for (int i = 0; i < 4; ++i) { acc[i][0] = pack2(b4.x, b4.y); acc[i][1] = pack2(b4.z, b4.w); }
             }
 #pragma unroll
             for (int ky = 0; ky < KS; ++ky) {
-              float4 h[KS + 6];
+              f32x2 h[KS + 6][2];
 #pragma unroll
-              for (int x = 0; x < KS + 6; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(ky * HW + x) * 128);
+              for (int x = 0; x < KS + 6; ++x) {
+                const float4 h4 = *reinterpret_cast<const float4*>(hb + (size_t)(ky * HW + x) * 128);
+                h[x][0] = pack2(h4.x, h4.y); h[x][1] = pack2(h4.z, h4.w);
+              }
 #pragma unroll
               for (int kx = 0; kx < KS; ++kx) {
                 const float4 w4 = *reinterpret_cast<const float4*>(wk + (ky * KS + kx) * cp);
+                const f32x2 w01 = pack2(w4.x, w4.y), w23 = pack2(w4.z, w4.w);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  a[i].x = fmaf(h[2 * i + kx].x, w4.x, a[i].x); a[i].y = fmaf(h[2 * i + kx].y, w4.y, a[i].y);
-                  a[i].z = fmaf(h[2 * i + kx].z, w4.z, a[i].z); a[i].w = fmaf(h[2 * i + kx].w, w4.w, a[i].w);
+                  acc[i][0] = fma2(h[2 * i + kx][0], w01, acc[i][0]);
+                  acc[i][1] = fma2(h[2 * i + kx][1], w23, acc[i][1]);
                 }
               }
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { unpack2(acc[i][0], a[i].x, a[i].y); unpack2(acc[i][1], a[i].z, a[i].w); }
           }
         } else if (valid) {
           const unsigned char* hb = halo + (size_t)c_slot * p.halo_bytes + hoff;
           const float* wk = w2s + c_s * 32 + ch * 4;
+          // the multiply-adds run as packed pairs (FFMA2: channels (0,1) and (2,3) of every 16-byte piece)
+          f32x2 acc[8][2];
           {
             const float4 b4 = *reinterpret_cast<const float4*>(wk + KS * KS * cp);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = b4;
+            for (int i = 0; i < 8; ++i) { acc[i][0] = pack2(b4.x, b4.y); acc[i][1] = pack2(b4.z, b4.w); }
           }
-          float4 wprev[KS > 0 ? KS : 1];
+          f32x2 wprev[KS > 0 ? KS : 1][2];
 #pragma unroll
           for (int hy = 0; hy <= KS; ++hy) {
-            float4 h[KS + 3];
+            f32x2 h[KS + 3][2];
 #pragma unroll
-            for (int x = 0; x < KS + 3; ++x) h[x] = *reinterpret_cast<const float4*>(hb + (size_t)(hy * HW + x) * 128);
+            for (int x = 0; x < KS + 3; ++x) {
+              const float4 h4 = *reinterpret_cast<const float4*>(hb + (size_t)(hy * HW + x) * 128);
+              h[x][0] = pack2(h4.x, h4.y); h[x][1] = pack2(h4.z, h4.w);
+            }
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx) {
               if (hy >= 1) {                                      // output row 1 sees this halo row as tap row hy - 1
-                const float4 w4 = KS == 3 ? wprev[kx] : *reinterpret_cast<const float4*>(wk + ((hy - 1) * KS + kx) * cp);
+                f32x2 w01, w23;
+                if (KS == 3) { w01 = wprev[kx][0]; w23 = wprev[kx][1]; }
+                else {
+                  const float4 w4 = *reinterpret_cast<const float4*>(wk + ((hy - 1) * KS + kx) * cp);
+                  w01 = pack2(w4.x, w4.y); w23 = pack2(w4.z, w4.w);
+                }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  a[4 + i].x = fmaf(h[i + kx].x, w4.x, a[4 + i].x); a[4 + i].y = fmaf(h[i + kx].y, w4.y, a[4 + i].y);
-                  a[4 + i].z = fmaf(h[i + kx].z, w4.z, a[4 + i].z); a[4 + i].w = fmaf(h[i + kx].w, w4.w, a[4 + i].w);
+                  acc[4 + i][0] = fma2(h[i + kx][0], w01, acc[4 + i][0]);
+                  acc[4 + i][1] = fma2(h[i + kx][1], w23, acc[4 + i][1]);
                 }
               }
               if (hy < KS) {                                      // output row 0: tap row hy
                 const float4 w4 = *reinterpret_cast<const float4*>(wk + (hy * KS + kx) * cp);
-                if (KS == 3) wprev[kx] = w4;
+                const f32x2 w01 = pack2(w4.x, w4.y), w23 = pack2(w4.z, w4.w);
+                if (KS == 3) { wprev[kx][0] = w01; wprev[kx][1] = w23; }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                  a[i].x = fmaf(h[i + kx].x, w4.x, a[i].x); a[i].y = fmaf(h[i + kx].y, w4.y, a[i].y);
-                  a[i].z = fmaf(h[i + kx].z, w4.z, a[i].z); a[i].w = fmaf(h[i + kx].w, w4.w, a[i].w);
+                  acc[i][0] = fma2(h[i + kx][0], w01, acc[i][0]);
+                  acc[i][1] = fma2(h[i + kx][1], w23, acc[i][1]);
                 }
               }
             }
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { unpack2(acc[i][0], a[i].x, a[i].y); unpack2(acc[i][1], a[i].z, a[i].w); }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&hempty_bar[c_slot]));   // this warp no longer reads the slot
@@ -836,10 +848,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float4 bia = col + 4 * j < 128 ? *reinterpret_cast<const float4*>(bias_s + col + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              o[j].x += __uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]) + bia.x;
-              o[j].y += __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]) + bia.y;
-              o[j].z += __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]) + bia.z;
-              o[j].w += __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]) + bia.w;
+              // o += (main + corr) + bias, as packed pairs (FADD2)
+              const f32x2 s01 = add2(add2(pack2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                                          pack2(__uint_as_float(w[4 * j]), __uint_as_float(w[4 * j + 1]))), pack2(bia.x, bia.y));
+              const f32x2 s23 = add2(add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                                          pack2(__uint_as_float(w[4 * j + 2]), __uint_as_float(w[4 * j + 3]))), pack2(bia.z, bia.w));
+              unpack2(add2(pack2(o[j].x, o[j].y), s01), o[j].x, o[j].y);
+              unpack2(add2(pack2(o[j].z, o[j].w), s23), o[j].z, o[j].w);
             }
           }
           if (c.act == YL_ACT_RELU) {
@@ -925,10 +940,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           float4* srow = reinterpret_cast<float4*>(stg + lane * TC_EPI_PITCH);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            srow[j] = make_float4(__uint_as_float(v[4 * j]) + __uint_as_float(w[4 * j]),
-                                  __uint_as_float(v[4 * j + 1]) + __uint_as_float(w[4 * j + 1]),
-                                  __uint_as_float(v[4 * j + 2]) + __uint_as_float(w[4 * j + 2]),
-                                  __uint_as_float(v[4 * j + 3]) + __uint_as_float(w[4 * j + 3]));
+            {
+              float4 sv;
+              unpack2(add2(pack2(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1])),
+                           pack2(__uint_as_float(w[4 * j]), __uint_as_float(w[4 * j + 1]))), sv.x, sv.y);
+              unpack2(add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
+                           pack2(__uint_as_float(w[4 * j + 2]), __uint_as_float(w[4 * j + 3]))), sv.z, sv.w);
+              srow[j] = sv;
+            }
         }
         __syncwarp();
         const int nb = chunk_n0 + col;                        // first global column of the block
