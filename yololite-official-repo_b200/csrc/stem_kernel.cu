@@ -132,16 +132,16 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
   unsigned char* planes = a1 + A1S * S2_A1_STAGE;           // 3 splits x 35904 B
   float* patch = reinterpret_cast<float*>(planes + 3 * S2_PLANE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(patch) + S2_PATCH_BYTES);
-  uint64_t* a1_full = bars;            // [2]  producers (8 warps) -> MMA
+  uint64_t* a1_full = bars;            // [2]  producers (4 warps of a group) -> MMA
   uint64_t* a1_empty = bars + 2;       // [2]  MMA commit -> producers
   uint64_t* acc1_full = bars + 4;      // [3]  MMA commit -> epilogue   (ring over the stem sub-tiles)
-  uint64_t* acc1_free = bars + 9;      // [3]  epilogue (8 warps) -> MMA
-  uint64_t* halo_full = bars + 14;     //      epilogue (8 warps) -> MMA
-  uint64_t* halo_free = bars + 15;     //      MMA commit -> epilogue
-  uint64_t* acc2_full = bars + 16;     // [2]  MMA commit -> epilogue
-  uint64_t* acc2_free = bars + 18;     // [2]  epilogue (8 warps) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
-  uint64_t* patch_full = bars + 21;    //      TMA complete_tx -> producers: the input patch of the next tile has landed
+  uint64_t* acc1_free = bars + 7;      // [3]  epilogue (8 warps) -> MMA
+  uint64_t* plane_full = bars + 10;    // [4]  epilogue (8 warps) -> MMA: parity plane pl of this tile's halo is complete
+  uint64_t* plane_free = bars + 14;    // [4]  MMA commit -> epilogue: conv2's taps on plane pl have read it
+  uint64_t* acc2_full = bars + 18;     // [2]  MMA commit -> epilogue
+  uint64_t* acc2_free = bars + 20;     // [2]  epilogue (8 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* patch_full = bars + 23;    //      TMA complete_tx -> producers: the input patch of the next tile has landed
   float* pws = reinterpret_cast<float*>(bars + 24);       // fused pointwise: 16 x 16 weights + 16 biases
   unsigned short* lut = reinterpret_cast<unsigned short*>(pws + 16 * 16 + 16);   // [S2_ROWS] row -> halo pixel (s2_row_pixel)
   const bool has_pw = p.pw != nullptr;
@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
     for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&a1_full[s]), S2_PROD_WARPS / 2); mbar_init(smem_u32(&a1_empty[s]), 1); }
     for (int j = 0; j < S2_ACC1_RING; ++j) { mbar_init(smem_u32(&acc1_full[j]), 1); mbar_init(smem_u32(&acc1_free[j]), S2_EPI_WARPS); }
     mbar_init(smem_u32(patch_full), 1);
-    mbar_init(smem_u32(halo_full), S2_EPI_WARPS);
-    mbar_init(smem_u32(halo_free), 1);
+    for (int pl = 0; pl < 4; ++pl) { mbar_init(smem_u32(&plane_full[pl]), S2_EPI_WARPS); mbar_init(smem_u32(&plane_free[pl]), 1); }
     // with the fused pointwise conv the two column-half warps of a lane quarter take alternate tiles (4 arrivals per buffer)
     for (int b = 0; b < 2; ++b) { mbar_init(smem_u32(&acc2_full[b]), 1); mbar_init(smem_u32(&acc2_free[b]), has_pw ? S2_EPI_WARPS / 2 : S2_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -219,6 +218,15 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)S2_PATCH_BYTES) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
                      ::"r"(smem_u32(patch)), "l"(&tmap), "r"(ixa), "r"(iy0), "r"(3 * b), "r"(bar) : "memory");
+        // There is one patch buffer, so this load's latency is exposed once per tile: pull the NEXT tile's patch into L2 now, its
+        // load then pays the L2 latency instead of the DRAM latency
+        const int nt = tile + (int)gridDim.x;
+        if (nt < tiles) {
+          const int b2 = nt / per_img, rem2 = nt - b2 * per_img;
+          const int ty2 = rem2 / p.tiles_x, tx2 = rem2 - ty2 * p.tiles_x;
+          asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
+                       ::"l"(&tmap), "r"(4 * S2_TW * tx2 - 4), "r"(4 * S2_TH * ty2 - 3), "r"(3 * b2) : "memory");
+        }
       }
     };
     issue_patch(blockIdx.x);
@@ -355,39 +363,50 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
           if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
         }
       };
-      auto gemm2 = [&](uint32_t it) {
+      // conv2 of tile `it`, the taps that read parity plane pl = 2 py + px: (0,0): taps (0,0) (0,2) (2,0) (2,2); (0,1): (0,1) (2,1);
+      // (1,0): (1,0) (1,2); (1,1): (1,1).  The planes complete in this order (GEMM1 rows are in plane order), so conv2 starts on
+      // plane 0 while the epilogue still writes planes 1-3, and releases every plane as soon as its own taps have read it: neither
+      // conv2 nor the wait for it sits between two tiles any more.
+      auto gemm2_plane = [&](uint32_t it, int pl) {
         const uint32_t b = it & 1u;
-        mbar_wait(smem_u32(&acc2_free[b]), ((it >> 1) & 1u) ^ 1u);
-        mbar_wait(smem_u32(halo_full), it & 1u);
+        if (pl == 0) mbar_wait(smem_u32(&acc2_free[b]), ((it >> 1) & 1u) ^ 1u);
+        mbar_wait(smem_u32(&plane_full[pl]), it & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d0 = tmem_base + ACC2_COL + S2_ACC2_COLS * b;
+        const int py = pl >> 1, px = pl & 1;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int ky = tap / 3, kx = tap - ky * 3, px = kx & 1;
+          const int ky = tap / 3, kx = tap - ky * 3;
+          if ((ky & 1) != py || (kx & 1) != px) continue;
           const int pw = px ? 8 : 9;
-          const int aoff = (s2_plane_off(ky & 1, px) + (ky >> 1) * pw + (kx >> 1)) * 64;
+          const int aoff = (s2_plane_off(py, px) + (ky >> 1) * pw + (kx >> 1)) * 64;
 #pragma unroll
           for (int ks = 0; ks < 2; ++ks) {
             const uint64_t db = dW2 + (uint64_t)((uint32_t)tap * w2_tap16 + (uint32_t)(ks * 2));
-            const uint32_t acc = (tap > 0 || ks > 0) ? 1u : 0u;
+            const uint32_t acc = (pl > 0 || tap > 0 || ks > 0) ? 1u : 0u;      // tap (0,0) of plane 0 is the first
             mma_bf16(d0, dP[px] + (uint64_t)((0 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2a, acc);
             mma_bf16(d0 + N2, dP[px] + (uint64_t)((1 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2b, 1u);
             mma_bf16(d0 + 2u * N2, dP[px] + (uint64_t)((2 * S2_PLANE_BYTES + aoff + ks * 32) >> 4), db, i2c, 1u);
           }
         }
-        mma_commit(smem_u32(halo_free));
-        mma_commit(smem_u32(&acc2_full[b]));
+        mma_commit(smem_u32(&plane_free[pl]));
+        if (pl == 3) mma_commit(smem_u32(&acc2_full[b]));
       };
+      // Issue order = the order in which the epilogue enables the pieces (it drains sub-tile j of a tile, then completes plane
+      // j - 1): G1(it,3) G1(it,4) G2(it).p0 G1(it+1,0) G2(it).p1 G1(it+1,1) G2(it).p2 G1(it+1,2) G2(it).p3; the accumulator ring
+      // holds 3 sub-tiles, so G1(., j) follows the drain of the sub-tile three before it.
       uint32_t it = 0;
+      gemm1(0, 3);
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        // The accumulator ring holds 3 of a tile's 5 stem sub-tiles, and the epilogue cannot drain the next tile's second
-        // sub-tile before conv2 of this tile has released the halo: issue three of the next tile's stem GEMMs, then this
-        // tile's conv2, then the remaining two.
         const bool more = tile + (int)gridDim.x < tiles;
-        if (it == 0) gemm1(0, S2_MT);
-        if (more) gemm1(0, S2_ACC1_RING);
-        gemm2(it);
-        if (more) gemm1(S2_ACC1_RING, S2_MT);
+        gemm1(3, 5);
+        gemm2_plane(it, 0);
+        if (more) gemm1(0, 1);
+        gemm2_plane(it, 1);
+        if (more) gemm1(1, 2);
+        gemm2_plane(it, 2);
+        if (more) gemm1(2, 3);
+        gemm2_plane(it, 3);
       }
     }
     __syncwarp();
@@ -515,7 +534,8 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&acc1_free[slot]));
         if (++slot == S2_ACC1_RING) { slot = 0; sphase ^= 1u; }
-        if (j == 0) mbar_wait(smem_u32(halo_free), (it & 1u) ^ 1u);   // conv2 of the previous tile has read the halo
+        // sub-tile j is the first to write plane j (rows 128 j ... straddle planes j - 1 and j): conv2 of the previous tile has read it
+        if (j < 4) mbar_wait(smem_u32(&plane_free[j]), (it & 1u) ^ 1u);
         // GEMM1 row q IS pixel q of the parity planes (s2_row_pixel): consecutive lanes write consecutive 64 B plane rows, whose
         // SWIZZLE_64B chunk positions make every 8-lane group of a 16 B store hit eight different bank groups
         const uint32_t q = (uint32_t)(j * 128 + q4 * 32 + lane);
@@ -541,10 +561,12 @@ __global__ void __launch_bounds__(S2_THREADS, 1) stem2_kernel(const Stem2Params 
           *reinterpret_cast<uint4*>(row + 2 * S2_PLANE_BYTES + d0) = make_uint4(o3[0], o3[1], o3[2], o3[3]);
           *reinterpret_cast<uint4*>(row + 2 * S2_PLANE_BYTES + d1) = make_uint4(o3[4], o3[5], o3[6], o3[7]);
         }
+        if (j >= 1) {                                          // plane j - 1 is complete (as far as this warp's rows go)
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&plane_full[j - 1]));
+        }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(halo_full));
       if (prev_tile >= 0) out_epi(it - 1, prev_tile);         // runs while the tensor core works on this tile's conv2
       prev_tile = tile;
     }
