@@ -465,9 +465,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       const bool valid2 = rp < p.tile_h;
       const uint32_t hoff2 = ((uint32_t)(2 * rp * HW + 2 * tx0) * 8u + (uint32_t)ch) * 16u;
       const int arow2 = rp * TW + tx0;
+      // j % HS, j / HS and j % nslab advance by 2 per iteration: kept as running counters (HS is 2 or 4; a division by a runtime
+      // value is ~60 dependent instructions at the head of every item)
+      int c_slot = grp & (HS - 1), c_s = grp % p.nslab;
+      uint32_t hround = (uint32_t)(grp / HS);
       for (int j = grp; j < total; j += 2) {
-        const int c_slot = j % HS, c_s = j % p.nslab, stage = j & 1;           // MODE 2 runs with 2 A stages
-        const uint32_t hphase = (uint32_t)(j / HS) & 1u, phase = (uint32_t)(j >> 1) & 1u;
+        const int stage = j & 1;                                           // MODE 2 runs with 2 A stages
+        const uint32_t hphase = hround & 1u, phase = (uint32_t)(j >> 1) & 1u;
         mbar_wait(smem_u32(&hfull_bar[c_slot]), hphase, p.dbg, 5u);          // this item's halo tile has landed
         float4 a[8];                                              // [row 0: 4 pixels][row 1: 4 pixels]
         if (p.dw_stride == 2) {
@@ -577,6 +581,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&full_bar[stage]));
+        c_slot += 2; if (c_slot >= HS) { c_slot -= HS; ++hround; }
+        c_s += 2; while (c_s >= p.nslab) c_s -= p.nslab;
       }
     }
   } else if (MODE == 0 && warp == TC_TMA_WARP) {
