@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
-echo "== pytest -m gpu" ; timeout 1500 python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
+echo "== pytest -m gpu" ; timeout 900 python -m pytest tests -m gpu -q --timeout 120 --timeout-method thread ${PYTEST_ARGS:-} 2>&1 | tail -60 | tee gpurun_out/pytest_gpu.log
 echo "== smoke" ; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee gpurun_out/smoke.log
-echo "== bench" ; timeout 600 python bench.py --steps 20 --warmup 5 --dump-ops gpurun_out/op_times.json 2>gpurun_out/bench.err | tee gpurun_out/bench.json
+echo "== bench" ; timeout 600 python bench.py --dump-ops gpurun_out/op_times.json 2>gpurun_out/bench.err | tee gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
