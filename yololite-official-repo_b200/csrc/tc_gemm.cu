@@ -795,6 +795,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
     // dense staging: N not a multiple of 4 (head outputs, 5+C channels), single chunk, plain [M][N] output
     const bool dense = p.dense_epi != 0;
     float* dstg = dense_stage + q * (32 * p.Nc);
+    bool dense_pending = false;                              // a bulk store of this warp's dense staging block may still be reading it
     const int vr = lane >> 3, vc = (lane & 7) * 4;            // vector path: rows vr + 4*it, columns vc..vc+3
     const int hw = c.Wout * c.Hout;
     int acc = p.epi2 ? grp : 0;
@@ -925,6 +926,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           while (ox >= c.Wout) { ox -= c.Wout; if (++oy == c.Hout) { oy = 0; if (b + 1 < c.B) ++b; } }
         }
       }
+      if (dense_pending) {                                     // the previous tile's bulk store has read the staging block
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        __syncwarp();
+        dense_pending = false;
+      }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.dbg, 17u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
@@ -1037,18 +1043,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));     // TMEM is drained: the MMA warp may reuse it
       if (dense) {
-        // rows of a warp are consecutive in memory ([M][N] row-major, one chunk): write them as one 16 B-aligned span
+        // rows of a warp are consecutive in memory ([M][N] row-major, one chunk): the staging block IS the memory image of the span
         float* dst = c.out + (size_t)mw * N;
         const int tot = rows_ok * N, tot4 = tot >> 2;
-        for (int i = lane; i < tot4; i += 32)
-          reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(dstg)[i];
-        for (int i = (tot4 << 2) + lane; i < tot; i += 32) dst[i] = dstg[i];
-        __syncwarp();
+        if (tot > 0 && (tot & 3) == 0 && ((reinterpret_cast<uintptr_t>(dst) | (uintptr_t)smem_u32(dstg)) & 15) == 0) {
+          // ... written by ONE bulk copy (32 rows x N x 4 B is a multiple of 16 for every N); the next tile waits for its read below
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(dstg)), "r"((uint32_t)tot * 4u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          dense_pending = true;
+        } else {
+          for (int i = lane; i < tot4; i += 32)
+            reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(dstg)[i];
+          for (int i = (tot4 << 2) + lane; i < tot; i += 32) dst[i] = dstg[i];
+          __syncwarp();
+        }
       }
       if (p.epi2) acc_phase ^= 1;                              // this group owns one accumulator
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_out && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all tensor stores are complete
+    if ((p.tma_out || p.dense_epi) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores are complete
   }
 
   // ---- teardown
