@@ -104,7 +104,7 @@ def main():
         L.check(lib.yl_run_op(ctypes.byref(op), blob.data_ptr(), x.data_ptr(), res.data_ptr() if res is not None else None,
                               up.data_ptr() if up is not None else None, out.data_ptr(), B, H, H,
                               up.shape[1] if up is not None else 0, up.shape[2] if up is not None else 0, a.tc, None))
-    for _ in range(3):
+    for _ in range(int(os.environ.get("YL_BENCH_OP_WARMUP", "3"))):
         run()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -156,12 +156,22 @@ __device__ __noinline__ float4 act4(float4 o, int act) {
   return o;
 }
 
+#ifdef YL_TIMELINE
+// diagnostic build only: CTA 0 stamps %globaltimer (ns) of a few events into the mapped debug words 16 + k (first occurrence only)
+#define YL_STAMP(k) do { if (blockIdx.x == 0 && blockIdx.y == 0 && p.dbg && p.dbg[16 + (k)] == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[16 + (k)] = t_; } } while (0)
+#define YL_STAMP_LAST(k) do { if (blockIdx.x == 0 && blockIdx.y == 0 && p.dbg) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); p.dbg[16 + (k)] = t_; } } while (0)
+#else
+#define YL_STAMP(k) do { } while (0)
+#define YL_STAMP_LAST(k) do { } while (0)
+#endif
+
 template <int MODE, int KS>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p, const __grid_constant__ CUtensorMap tmap,
                                                                 const __grid_constant__ CUtensorMap omap) {
   extern __shared__ unsigned char smem_unaligned[];
   unsigned char* smem = smem_unaligned + ((1024u - (smem_u32(smem_unaligned) & 1023u)) & 1023u);   // SWIZZLE_128B atoms
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) YL_STAMP(0);
   const ConvParams& c = p.c;
   const int M = (int)p.M;
 
@@ -263,10 +273,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
   // PDL trigger AFTER this CTA holds its tensor memory: the next kernel's CTAs may now become resident and run their own
   // prologue while this kernel works (they wait for our completion before reading activations).  Triggering before the TMEM
   // allocation could let a dependent CTA grab columns first and then block this CTA in tcgen05.alloc for ever.
+  if (threadIdx.x == 0) YL_STAMP(1);            // prologue done
   pdl_launch_dependents();
   // everything above touched only constant data (weights, biases) and this CTA's shared memory / TMEM: with PDL it overlapped
   // the previous kernel's tail.  From here on activations written by earlier kernels are read.
   pdl_wait();
+  if (threadIdx.x == 0) YL_STAMP(2);            // dependency resolved
 
   if (warp < p.prod_warps) {
     // =============================== producers ===============================
@@ -292,6 +304,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       uint32_t phase = 0;
       for (int j = 0; j < total; ++j) {
         mbar_wait(smem_u32(&wfull_bar[stage]), phase, p.dbg, 1u);
+        if (threadIdx.x == 0) YL_STAMP(3);      // first A slab landed
         unsigned char* st = a_ring + (size_t)stage * TC_STAGE_BYTES;
         for (int ps = 0; ps < npass; ++ps) {
           float4 a[4];
@@ -750,6 +763,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         uint32_t first = 0;
         for (int s = 0; s < p.nslab; ++s) {
           mbar_wait(smem_u32(&full_bar[stage]), phase, p.dbg, 14u);
+          YL_STAMP(4);                          // MMA issuer: first operand stage ready
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a12 = smem_u32(a_ring + (size_t)stage * TC_STAGE_BYTES);      // rows: [a1 (64 B) | a2 (64 B)], SWIZZLE_128B
           const uint32_t a3 = a12 + (uint32_t)TC_P12_BYTES;                            // rows: a3 (64 B), SWIZZLE_64B
@@ -775,6 +789,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         mma_commit(smem_u32(&tfull_bar[acc]));               // accumulators complete
+        YL_STAMP(5);                            // first tile's MMAs issued
+        YL_STAMP_LAST(8);                       // last tile's MMAs issued
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -827,6 +843,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
           up_row = c.up + ((size_t)(b * c.Hu + nearest_src(oy, c.Hu, c.Hout)) * c.Wu + nearest_src(ox, c.Wu, c.Wout)) * N + chunk_n0;
         }
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.dbg, 16u);
+        if (q == 0 && lane == 0) YL_STAMP(6);   // first accumulator ready
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
         for (int col = 0; col < p.Nc; col += 32) {
@@ -932,6 +949,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
         dense_pending = false;
       }
       mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase, p.dbg, 17u);
+      if (q == 0 && lane == 0) YL_STAMP(6);     // first accumulator ready
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * (uint32_t)(2 * p.Nc);
       for (int col = 0; col < p.Nc; col += 32) {
@@ -1065,10 +1083,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
       if (p.epi2) acc_phase ^= 1;                              // this group owns one accumulator
       else if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (q == 0 && lane == 0) YL_STAMP_LAST(9);    // epilogue: last tile handed to the store engine
     if ((p.tma_out || p.dense_epi) && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all bulk stores are complete
+    if (q == 0 && lane == 0) YL_STAMP_LAST(10);   // stores complete
   }
 
   // ---- teardown
+  if (threadIdx.x == 0) YL_STAMP_LAST(11);     // reached the teardown barrier
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == TC_MMA_WARP) {
