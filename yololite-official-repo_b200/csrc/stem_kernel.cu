@@ -14,10 +14,12 @@
 //               constant-1 column that carries the folded BN bias, padded to 32; all patch offsets are immediates) for
 //               five 128-row tiles covering the 33 x 17 halo of stem output pixels.  The rows are in PLANE order (row q
 //               = pixel q of the parity planes below), so the epilogue's plane stores are bank-conflict free;
-//   warp  16    one thread issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128, N = 96|64|32, K = 32) into a ring of
-//               three TMEM accumulator triples, GEMM2 = conv2 as nine per-tap GEMMs (M = 128, N = 3|2|1 x N2, K = 32);
-//   warps 0-7   epilogue: TMEM -> ReLU -> bf16 triple -> shared-memory halo stored as four parity planes
-//               (row parity x column parity); then conv2's accumulator -> bias + ReLU -> NHWC global stores.
+//   warp  16    one elected thread (elect.sync, see launch.cuh) issues tcgen05.mma.kind::f16 (bf16): GEMM1 = stem (M = 128,
+//               N = 96|64|32, K = 32) into a ring of three TMEM accumulator triples, GEMM2 = conv2 as nine per-tap GEMMs
+//               (M = 128, N = 3|2|1 x N2, K = 32), issued plane by plane as the epilogue completes the parity planes;
+//   warps 0-7   epilogue: TMEM -> ReLU folded into round-toward-zero bf16 splits -> shared-memory halo stored as four parity
+//               planes (row parity x column parity, per-plane full / free mbarriers); then conv2's accumulator -> bias + ReLU
+//               (-> fused 16x16 pointwise conv) -> NHWC global stores.
 // GEMM2 has NO im2col copy: for tap (ky, kx) the A operand of the 16x8 tile is the parity plane (ky&1, kx&1) shifted
 // by (ky>>1, kx>>1) pixels, which a K-major SWIZZLE_64B descriptor addresses directly (8-row atoms = 8 consecutive
 // output columns, stride-byte-offset = plane pitch).  The hardware swizzle is a function of the shared-memory ADDRESS
