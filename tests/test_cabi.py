@@ -66,3 +66,24 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 with open(os.path.join(root, f)) as fh:
                     assert not re.search(r"^\s*(from|import)\s+oracle", fh.read(), flags=re.M), f
+
+
+def test_fused_stem_row_order_enumerates_the_halo_plane_by_plane():
+    """GEMM1 rows of the fused stem kernel are in PARITY-PLANE order (csrc/stem_kernel.cu: s2_row_pixel): row q is pixel q of the
+    four planes (row parity, column parity) of the 33 x 17 stem-output halo, pitches 9 / 8, offsets 0 / 153 / 289 / 433 -- the
+    layout conv2's shifted SWIZZLE_64B descriptors address.  Host-side view through yl_stat; no GPU needed."""
+    import yololite_b200 as y
+    lib = y.lib()
+    seen = {}
+    for q in range(640):
+        v = lib.yl_stat(b"stem_row_pixel%d" % q)
+        if q >= 561:
+            assert v == 0xFFFF, (q, v)
+            continue
+        hy, hx = v & 0xFF, v >> 8
+        assert 0 <= hy < 33 and 0 <= hx < 17
+        off = {(0, 0): 0, (0, 1): 153, (1, 0): 289, (1, 1): 433}[(hy & 1, hx & 1)]
+        assert q == off + (hy >> 1) * (8 if hx & 1 else 9) + (hx >> 1), (q, hy, hx)
+        seen[(hy, hx)] = q
+    assert len(seen) == 33 * 17
+    assert lib.yl_stat(b"stem_row_pixel640") == -1

@@ -514,6 +514,7 @@ long long yl_stat(const char* key) {
   if (!std::strcmp(key, "graph_launches")) return yl::g_graph_launches;
   if (!std::strcmp(key, "graph_captures")) return yl::g_graph_captures;
   if (!std::strcmp(key, "prepares")) return yl::g_prepares;
+  if (!std::strncmp(key, "stem_row_pixel", 14)) return yl::stem2_row_pixel(atoi(key + 14));
   if (!std::strcmp(key, "debug_reset")) { unsigned long long* w = yl::debug_words(); if (w) memset(w, 0, 32 * sizeof(unsigned long long)); return 0; }
   if (!std::strncmp(key, "trap_word", 9)) { unsigned long long* w = yl::debug_words(); const int i = atoi(key + 9) & 31; return w ? (long long)w[i] : 0; }
   return -1;

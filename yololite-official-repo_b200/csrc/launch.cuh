@@ -149,5 +149,6 @@ struct Stem2Launch {
 };
 int stem2_prepare(const ConvParams& c, const float* wimg, int sm_count, Stem2Launch* L);
 int stem2_launch(const Stem2Launch& L, cudaStream_t st, int pdl);
+int stem2_row_pixel(int q);            // GEMM1 row q of the fused stem -> halo pixel hy | hx << 8 (0xFFFF: padding row, -1: out of range)
 
 }  // namespace yl

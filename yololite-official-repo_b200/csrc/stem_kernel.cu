@@ -642,6 +642,9 @@ int stem2_prepare(const ConvParams& c, const float* wimg, int sm_count, Stem2Lau
   return 0;
 }
 
+// host-side view of the GEMM1 row order (tests/test_cabi.py checks that it enumerates the 33 x 17 halo plane by plane)
+int stem2_row_pixel(int q) { return q >= 0 && q < S2_ROWS ? (int)s2_row_pixel(q) : -1; }
+
 int stem2_launch(const Stem2Launch& L, cudaStream_t st, int pdl) {
   cudaError_t e;
   if (L.p.a1_stages == 2) e = launch_ex(stem2_kernel<2>, dim3(L.grid), S2_THREADS, L.smem, st, pdl, L.p, L.tmap);
