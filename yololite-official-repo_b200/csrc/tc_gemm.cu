@@ -544,12 +544,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
 #pragma unroll
             for (int kx = 0; kx < KS; ++kx) {
               if (hy >= 1) {                                      // output row 1 sees this halo row as tap row hy - 1
-                f32x2 w01, w23;
-                if (KS == 3) { w01 = wprev[kx][0]; w23 = wprev[kx][1]; }
-                else {
-                  const float4 w4 = *reinterpret_cast<const float4*>(wk + ((hy - 1) * KS + kx) * cp);
-                  w01 = pack2(w4.x, w4.y); w23 = pack2(w4.z, w4.w);
-                }
+                const f32x2 w01 = wprev[kx][0], w23 = wprev[kx][1];      // tap row hy - 1: kept from the previous halo row
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   acc[4 + i][0] = fma2(h[i + kx][0], w01, acc[4 + i][0]);
@@ -559,7 +554,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
               if (hy < KS) {                                      // output row 0: tap row hy
                 const float4 w4 = *reinterpret_cast<const float4*>(wk + (hy * KS + kx) * cp);
                 const f32x2 w01 = pack2(w4.x, w4.y), w23 = pack2(w4.z, w4.w);
-                if (KS == 3) { wprev[kx][0] = w01; wprev[kx][1] = w23; }
+                wprev[kx][0] = w01; wprev[kx][1] = w23;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                   acc[i][0] = fma2(h[i + kx][0], w01, acc[i][0]);
