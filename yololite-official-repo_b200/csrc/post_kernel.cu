@@ -84,6 +84,10 @@ __device__ __forceinline__ float4 decode_box(float tx, float ty, float tw, float
 }
 
 // suppress j by i?  torchvision CPU nms: ovr = inter / (iarea + areas[j] - inter); ovr > thr (double)
+// Device-scope release / acquire fence (the ticket protocol needs no more: writes -> CTA barrier -> fence -> ticket atomic on the
+// producer side, ticket atomic -> fence -> CTA barrier -> reads through L2 on the consumer side); __threadfence() is fence.sc.gpu.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 __device__ __forceinline__ bool iou_gt(const float4& a, float area_a, const float4& b, double thr) {
   const float area_b = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
   const float w = fmaxf(0.f, __fsub_rn(fminf(a.z, b.z), fmaxf(a.x, b.x)));
@@ -171,19 +175,20 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
   }
 
   // ---------------- ticket: is this the last tile of image b?
-  __threadfence();
+  // the CTA barrier orders every thread's candidate writes before thread 0, whose (cumulative) fence orders them before its ticket
   __syncthreads();
   if (tid == 0) {
+    fence_acq_rel_gpu();
     const int ticket = atomicAdd(&p.done[b], 1);
     s_last = (ticket == tiles_per_image - 1);
     if (s_last) {
-      __threadfence();
+      fence_acq_rel_gpu();
       s_M = atomicAdd(&p.count[b], 0);
     }
   }
   __syncthreads();
   if (!s_last) return;
-  __threadfence();
+  fence_acq_rel_gpu();
 
   // ---------------- phase 2: sort + per-class NMS + compaction, one CTA for the whole image
   const int M = s_M;
@@ -191,11 +196,14 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
   const float4* cbox = p.cbox + (size_t)b * p.N;
   unsigned long long* keys;
   unsigned char* flags;        // 0 = alive/undecided, 1 = suppressed, 2 = kept
+  float4* sbox = nullptr;      // boxes of the sorted candidates, when they fit next to keys and flags (the usual detection case)
   if (M <= p.smem_keys) {
     keys = reinterpret_cast<unsigned long long*>(smem_raw);
     flags = smem_raw + (size_t)p.smem_keys * 8;
     int P = 1;
     while (P < M) P <<= 1;
+    const size_t boff = (size_t)(P < 2 ? 2 : P) * 8;         // 16-byte aligned, past the P sorted keys
+    if (boff + (size_t)M * 16 <= (size_t)p.smem_keys * 8) sbox = reinterpret_cast<float4*>(smem_raw + boff);
     for (int i = tid; i < P; i += POST_THREADS) keys[i] = i < M ? __ldcg(gkeys + i) : ~0ull;
     __syncthreads();
     for (int k = 2; k <= P; k <<= 1) {
@@ -224,18 +232,31 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
     __syncthreads();
   }
   for (int i = tid; i < M; i += POST_THREADS) flags[i] = 0;
+  if (sbox)                    // one parallel gather of the candidates' boxes instead of a global gather per class segment
+    for (int i = tid; i < M; i += POST_THREADS) sbox[i] = __ldcg(cbox + key_anchor(keys[i]));
   __syncthreads();
 
-  // ---- greedy NMS, one warp per class segment
+  // ---- greedy NMS, one warp per class segment.  Every warp walks ALL 32-candidate chunks and takes the segments whose ordinal is
+  // congruent to its index: at a detection threshold there are ~100 candidates in ~60 classes, and handing out segments by the
+  // chunk their first candidate sits in left those ~60 segments to 3 of the 8 warps (21 of the kernel's 49 us, in-kernel
+  // %globaltimer stamps of scripts/timeline_post.py).
   const double thr = p.iou;
-  for (int base = warp * 32; base < M; base += (POST_THREADS / 32) * 32) {
+  int seg_ord = 0;                                           // segments that start before the current chunk
+  for (int base = 0; base < M; base += 32) {
     const int pos = base + lane;
     const bool is_start = pos < M && (pos == 0 || key_cls(keys[pos]) != key_cls(keys[pos - 1]));
-    unsigned starts = __ballot_sync(0xffffffffu, is_start);
+    const unsigned all_starts = __ballot_sync(0xffffffffu, is_start);
+    unsigned starts = all_starts;
     while (starts) {
-      const int s = base + __ffs(starts) - 1;
+      const int bit = __ffs(starts) - 1;
       starts &= starts - 1;
+      if (((seg_ord + __popc(all_starts & ((1u << bit) - 1u))) & (POST_THREADS / 32 - 1)) != warp) continue;
+      const int s = base + bit;
       const int c = key_cls(keys[s]);
+      if (s + 1 >= M || key_cls(keys[s + 1]) != c) {         // a class with ONE candidate: kept, nothing to suppress
+        if (lane == 0) flags[s] = 2;
+        continue;
+      }
       // segment end: first position with a different class (binary search, uniform across the warp)
       int lo = s + 1, hi = M;
       while (lo < hi) {
@@ -252,7 +273,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
         for (int r = 0; r < REG_SEG; ++r) {
           const int q = s + lane + 32 * r;
           if (q < e) {
-            bx[r] = __ldcg(cbox + key_anchor(keys[q]));
+            bx[r] = sbox ? sbox[q] : __ldcg(cbox + key_anchor(keys[q]));
             ar[r] = __fmul_rn(__fsub_rn(bx[r].z, bx[r].x), __fsub_rn(bx[r].w, bx[r].y));
           } else {
             bx[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -304,12 +325,12 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
             break;
           }
           ++kept;
-          const float4 bi = __ldcg(cbox + key_anchor(keys[i]));
+          const float4 bi = sbox ? sbox[i] : __ldcg(cbox + key_anchor(keys[i]));
           const float ai = __fmul_rn(__fsub_rn(bi.z, bi.x), __fsub_rn(bi.w, bi.y));
           if (lane == 0) flags[i] = 2;
           for (int j = i + 1 + lane; j < e; j += 32) {
             if (!flags[j]) {
-              const float4 bj = __ldcg(cbox + key_anchor(keys[j]));
+              const float4 bj = sbox ? sbox[j] : __ldcg(cbox + key_anchor(keys[j]));
               if (iou_gt(bi, ai, bj, thr)) flags[j] = 1;
             }
           }
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
         __syncwarp();
       }
     }
+    seg_ord += __popc(all_starts);
   }
   __syncthreads();
 
@@ -340,7 +362,7 @@ __global__ void __launch_bounds__(POST_THREADS) post_kernel(PostParams p) {
         const unsigned long long key = keys[pos];
         const int n = key_anchor(key);
         const size_t q = (size_t)b * p.cap + o;
-        const float4 bx = __ldcg(cbox + n);
+        const float4 bx = sbox ? sbox[pos] : __ldcg(cbox + n);
         if (p.boxes) reinterpret_cast<float4*>(p.boxes)[q] = bx;
         if (p.scores) p.scores[q] = key_score(key);
         if (p.classes) p.classes[q] = key_cls(key);
