@@ -872,8 +872,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_conv_kernel(const TcParams p
                                           pack2(__uint_as_float(w[4 * j]), __uint_as_float(w[4 * j + 1]))), pack2(bia.x, bia.y));
               const f32x2 s23 = add2(add2(pack2(__uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])),
                                           pack2(__uint_as_float(w[4 * j + 2]), __uint_as_float(w[4 * j + 3]))), pack2(bia.z, bia.w));
-              unpack2(add2(pack2(o[j].x, o[j].y), s01), o[j].x, o[j].y);
-              unpack2(add2(pack2(o[j].z, o[j].w), s23), o[j].z, o[j].w);
+              if (MODE == 0 && c.up) {          // + the upsampled coarser level already in o
+                unpack2(add2(pack2(o[j].x, o[j].y), s01), o[j].x, o[j].y);
+                unpack2(add2(pack2(o[j].z, o[j].w), s23), o[j].z, o[j].w);
+              } else {
+                unpack2(s01, o[j].x, o[j].y);
+                unpack2(s23, o[j].z, o[j].w);
+              }
             }
           }
           if (c.act == YL_ACT_RELU) {
