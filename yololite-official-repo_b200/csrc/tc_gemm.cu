@@ -24,6 +24,10 @@
 //              ReLU/SiLU, TMA tensor stores / 16 B stores (head layout [B,A,S,S,5+C] written directly).
 // The weight image (three bf16 splits, pre-swizzled on the host) stays resident in shared memory for the CTA's lifetime or
 // is streamed per K-slab.  All waits are bounded: a protocol bug traps instead of hanging the GPU.
+// Resource notes: 448 threads x 128 registers and up to ~220 KB of shared memory -- one CTA per SM, no co-residency with the next
+// kernel (PDL only overlaps its prologue on SMs that have already drained).  The single-thread roles are guarded with elect.sync
+// (launch.cuh: elect_one), not `lane == 0`.  The shared-memory data pipe (LSU + tensor-core operand reads, 64-85 % busy) is the
+// binding resource of the large-map shapes; the epilogue is on their critical path (DESIGN.md section 4 lists what was measured).
 #include <cuda.h>
 
 #include <cstdlib>
